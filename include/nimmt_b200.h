@@ -1,0 +1,156 @@
+/*
+ * nimmt_b200.h — C ABI of the B200-native 6 nimmt! hot path.
+ *
+ * This is the whole drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * The reference (coolo/rl-6-nimmt) is pure Python and has no FFI of its own; each entry
+ * point below replaces a Python method of the reference, cited as file:line relative to
+ * the reference repository.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - All `state`, input and output pointers are DEVICE pointers owned by the caller
+ *     (in this repo: torch.Tensor storage).  The library never allocates, frees or keeps
+ *     a pointer beyond the stream work it enqueues.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls only enqueue;
+ *     they never synchronise.  Re-entrant; no global mutable state.
+ *   - Return value: NIMMT_OK (0) or a negative NIMMT_E_* code.  Nothing throws.
+ *   - Cards are 0-based (0..103) as in the reference (printed 1-based, env.py:244).
+ *   - num_rows = 4, num_cards = 104, threshold = 6, hand size 10 are compiled in; they are
+ *     the only values any reference caller uses (agents/mcts.py:21-23, play.py:17).
+ *   - num_players P in [1, 10] (env.py:19-21: 10 P + 4 <= 104).
+ *
+ * Packed game state (HBM layout).  For a batch of B games:
+ *     uint4 hand[P][B]   128-bit word per (player, game): bits 0..103 = cards held,
+ *                        bits 120..127 = that player's cumulative Hornochsen (<= 171)
+ *     uint4 rows_a[B]    bytes 0..15 of the 24-byte row block
+ *     uint2 rows_b[B]    bytes 16..23 of the row block
+ *   row block = 4 rows x 6 bytes: 5 card slots (oldest first) + 1 meta byte
+ *   (bits 0..2 = cards in the row, bits 3..7 = bull-head sum of the row, <= 27).
+ *   Total (16 P + 24) B bytes, structure-of-arrays so that a warp's accesses are contiguous.
+ */
+#ifndef NIMMT_B200_H
+#define NIMMT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NIMMT_API __attribute__((visibility("default")))
+#else
+#define NIMMT_API
+#endif
+
+#define NIMMT_OK 0
+#define NIMMT_E_BADARG (-1)     /* NULL pointer, bad player count, negative size, bad dtype */
+#define NIMMT_E_ALIGN (-2)      /* state pointer not 16-byte aligned */
+#define NIMMT_E_CUDA (-3)       /* kernel launch failed; see nimmt_last_cuda_error() */
+#define NIMMT_E_UNSUPPORTED (-4)
+
+#define NIMMT_NUM_ROWS 4
+#define NIMMT_NUM_CARDS 104
+#define NIMMT_THRESHOLD 6
+#define NIMMT_HAND 10
+#define NIMMT_MAX_PLAYERS 10
+
+/* observation element types for nimmt_observe */
+#define NIMMT_DT_I8 0
+#define NIMMT_DT_I16 1
+#define NIMMT_DT_F32 2
+#define NIMMT_DT_I64 3          /* the reference's dtype (np.hstack promotion, env.py:200) */
+
+/* ABI version of this header; bumped on any signature/layout change. */
+NIMMT_API int nimmt_abi_version(void);
+
+/* Text of the last CUDA error seen by this thread's calls ("" if none). */
+NIMMT_API const char *nimmt_last_cuda_error(void);
+
+/* Bytes of packed state for B games of P players: (16 P + 24) B.  Replaces the list
+ * allocations of SechsNimmtEnv.__init__ (env.py:30-32). Returns 0 on bad arguments. */
+NIMMT_API size_t nimmt_state_bytes(int64_t num_games, int num_players);
+
+/* Length of one observation vector: 47, or 35 without summaries (env.py:37). */
+NIMMT_API int nimmt_obs_len(int include_summaries);
+
+/* Bull heads of one card — SechsNimmtEnv._card_value (env.py:224-239). Host function. */
+NIMMT_API int nimmt_card_value(int card);
+
+/* SechsNimmtEnv.reset / _deal (env.py:43-51, 99-112), batched: deals every game from a
+ * counter-based RNG keyed by (seed, game0 + b), so results do not depend on launch geometry
+ * or on how games are split over GPUs.  Hands are uniform 10-subsets, rows uniform single
+ * cards, all distinct; scores zero. */
+NIMMT_API int nimmt_deal(void *state, int64_t num_games, int num_players, uint64_t seed, uint64_t game0, void *stream);
+
+/* SechsNimmtEnv._deal given the shuffled decks (env.py:103-112): perm is uint8 [B][104];
+ * hand p = perm[10p .. 10p+9], row r = perm[103 - r].  Lets a host that shuffles with the
+ * reference's own RNG reproduce the reference's deals bit for bit. */
+NIMMT_API int nimmt_deal_from_perm(void *state, const uint8_t *perm, int64_t num_games, int num_players, void *stream);
+
+/* SechsNimmtEnv.reset_to (env.py:53-62): board is int8 [B][4][6], hands int8 [B][P][10],
+ * both -1 padded exactly like the observation layout (env.py:191-194, 209-210).  Copies (the
+ * reference aliases the caller's lists).  Scores zero.  If `invalid` (uint8 [B]) is not NULL it
+ * receives 1 for games whose input was malformed (empty row, > 5 cards in a row, card out of
+ * range, duplicate card); such games are still written, with the malformed cards dropped. */
+NIMMT_API int nimmt_reset_to(void *state, const int8_t *board, const int8_t *hands, uint8_t *invalid,
+                   int64_t num_games, int num_players, void *stream);
+
+/* SechsNimmtEnv.step without the observation rebuild (env.py:64-77, 114-172, 214-249):
+ *   actions  uint8 [B][P]  card chosen by each player
+ *   rewards  int8  [B][P]  minus the bull heads taken this step (<= 0)          (env.py:169)
+ *   done     uint8 [B]     player 0's hand is empty                              (env.py:246-249)
+ *   illegal  uint8 [B]     may be NULL; 1 if some card was not in its owner's hand — that game
+ *                          is left untouched and its rewards are 0 (env.py:68-69 raises
+ *                          InvalidMoveException before any mutation) */
+NIMMT_API int nimmt_step(void *state, const uint8_t *actions, int8_t *rewards, uint8_t *done, uint8_t *illegal,
+               int64_t num_games, int num_players, void *stream);
+
+/* SechsNimmtEnv._create_states (env.py:174-212): obs [B][P][L] of `dtype`, L = nimmt_obs_len();
+ * layout [hand10 | P | (len4 top4 sum4)? | board 4x6], -1 padded.  The legal actions of player p
+ * are the non-negative entries of obs[b][p][0..9] (env.py:209).  n_legal (uint8 [B][P]) may be
+ * NULL. */
+NIMMT_API int nimmt_observe(const void *state, void *obs, uint8_t *n_legal, int64_t num_games, int num_players,
+                  int include_summaries, int dtype, void *stream);
+
+/* Cumulative Hornochsen per player, SechsNimmtEnv._scores (env.py:32,167): uint8 [B][P]. */
+NIMMT_API int nimmt_scores(const void *state, uint8_t *scores, int64_t num_games, int num_players, void *stream);
+
+/* DrunkHamster.forward (agents/random.py:8-10) for every player of every game: a uniformly
+ * random card of each hand, keyed by (seed, game0 + b, turn).  Empty hands yield 255. */
+NIMMT_API int nimmt_random_actions(const void *state, uint8_t *actions, int64_t num_games, int num_players,
+                         uint64_t seed, uint32_t turn, uint64_t game0, void *stream);
+
+/* nimmt_random_actions followed by nimmt_step in one kernel (random-vs-random play,
+ * play.py:36-45 with DrunkHamster agents).  `actions` may be NULL (not recorded). */
+NIMMT_API int nimmt_step_random(void *state, uint8_t *actions, int8_t *rewards, uint8_t *done,
+                      int64_t num_games, int num_players, uint64_t seed, uint32_t turn, uint64_t game0,
+                      void *stream);
+
+/* One root position of a Monte-Carlo search decision (BaseMCAgent state, agents/mcts.py:43-89). */
+typedef struct nimmt_root {
+    uint32_t own[4];        /* 104-bit mask of the deciding player's hand (legal_actions)       */
+    uint32_t available[4];  /* 104-bit mask of BaseMCAgent.available_cards (agents/mcts.py:62-73) */
+    uint8_t rows[4][6];     /* board rows as in the observation, 255-padded (mcts.py:75-85)     */
+    uint8_t num_players;    /* int(state[10]) (mcts.py:87-89)                                    */
+    uint8_t pad[7];
+} nimmt_root;               /* 64 bytes */
+
+/* BaseMCAgent._mcts with MCSAgent._choose_action_mc (agents/mcts.py:91-154, 187-188), batched
+ * over D decisions: for every root and every legal first card, `rollouts_per_action` uniform
+ * random playouts (stratified instead of the reference's uniform first-card choice; the law of
+ * the outcome given the first card is identical — DESIGN.md §5).
+ *   stats int64 [D][10][3] += (sum outcome, sum outcome^2, count) per first card, indexed by the
+ *   card's rank within the own hand (ascending).  The caller zeroes stats.
+ * All roots of one call share `num_players` (roots whose own num_players differs, or whose
+ * available set is smaller than (P-1) * |own|, are skipped: their stats stay zero).
+ * Rollout ids are striped over `world` ranks (id mod world == rank); summing the stats of all
+ * ranks gives the same integers for any world size. */
+NIMMT_API int nimmt_mcs_rollouts(const nimmt_root *roots, int num_roots, int num_players, int64_t rollouts_per_action,
+                                 uint64_t seed, int rank, int world, int64_t *stats, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIMMT_B200_H */

@@ -1,0 +1,109 @@
+// abi_common.cuh — shared by the translation units that implement include/nimmt_b200.h:
+// packed-state plane I/O, argument checks, the per-player-count dispatch.
+#pragma once
+#include <cstdio>
+
+#include "../../include/nimmt_b200.h"
+#include "step.cuh"
+
+namespace nimmt {
+
+constexpr int kStepThreads = 128;
+
+template <int P>
+__device__ __forceinline__ void load_game(const StateView& s, int64_t g, Game<P>& gm) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) gm.hand[p] = s.hand[(int64_t)p * s.B + g];
+    load_rows(s, g, gm.board);
+}
+
+template <int P>
+__device__ __forceinline__ void store_game(const StateView& s, int64_t g, const Game<P>& gm) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) s.hand[(int64_t)p * s.B + g] = gm.hand[p];
+    store_rows(s, g, gm.board);
+}
+
+// P consecutive bytes at base + g * P, using the widest access the alignment of g * P guarantees
+// (base is 16-byte aligned; checked in the C entry points).
+template <int P>
+__device__ __forceinline__ void load_bytes(const uint8_t* base, int64_t g, int (&v)[P]) {
+    const uint8_t* p = base + g * P;
+    if constexpr (P % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < P / 4; ++i) {
+            const uint32_t w = reinterpret_cast<const uint32_t*>(p)[i];
+            v[4 * i] = w & 0xFF; v[4 * i + 1] = (w >> 8) & 0xFF; v[4 * i + 2] = (w >> 16) & 0xFF; v[4 * i + 3] = w >> 24;
+        }
+    } else if constexpr (P % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < P / 2; ++i) {
+            const uint32_t w = reinterpret_cast<const uint16_t*>(p)[i];
+            v[2 * i] = w & 0xFF; v[2 * i + 1] = w >> 8;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) v[i] = p[i];
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void store_bytes(uint8_t* base, int64_t g, const int (&v)[P]) {
+    uint8_t* p = base + g * P;
+    if constexpr (P % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < P / 4; ++i)
+            reinterpret_cast<uint32_t*>(p)[i] = (uint32_t)(v[4 * i] & 0xFF) | ((uint32_t)(v[4 * i + 1] & 0xFF) << 8) |
+                                                ((uint32_t)(v[4 * i + 2] & 0xFF) << 16) | ((uint32_t)(v[4 * i + 3] & 0xFF) << 24);
+    } else if constexpr (P % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < P / 2; ++i)
+            reinterpret_cast<uint16_t*>(p)[i] = (uint16_t)((v[2 * i] & 0xFF) | ((v[2 * i + 1] & 0xFF) << 8));
+    } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) p[i] = (uint8_t)v[i];
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// host-side helpers of the C entry points
+// ------------------------------------------------------------------------------------------
+extern thread_local char g_last_error[256];  // defined in env_reset.cu
+
+inline int check_launch() {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_last_error, sizeof(g_last_error), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+        return NIMMT_E_CUDA;
+    }
+    return NIMMT_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int check_common(const void* state, int64_t B, int P) {
+    if (!state || B < 0 || P < 1 || P > kMaxPlayers) return NIMMT_E_BADARG;
+    if (!aligned16(state)) return NIMMT_E_ALIGN;
+    if (B > (int64_t)INT32_MAX * 64) return NIMMT_E_BADARG;
+    return NIMMT_OK;
+}
+
+#define NIMMT_DISPATCH_P(P_, ...)                              \
+    switch (P_) {                                              \
+        case 1: { constexpr int P = 1; __VA_ARGS__; } break;   \
+        case 2: { constexpr int P = 2; __VA_ARGS__; } break;   \
+        case 3: { constexpr int P = 3; __VA_ARGS__; } break;   \
+        case 4: { constexpr int P = 4; __VA_ARGS__; } break;   \
+        case 5: { constexpr int P = 5; __VA_ARGS__; } break;   \
+        case 6: { constexpr int P = 6; __VA_ARGS__; } break;   \
+        case 7: { constexpr int P = 7; __VA_ARGS__; } break;   \
+        case 8: { constexpr int P = 8; __VA_ARGS__; } break;   \
+        case 9: { constexpr int P = 9; __VA_ARGS__; } break;   \
+        case 10: { constexpr int P = 10; __VA_ARGS__; } break; \
+        default: return NIMMT_E_BADARG;                        \
+    }
+
+inline unsigned blocks_for(int64_t B, int threads) { return (unsigned)((B + threads - 1) / threads); }
+
+}  // namespace nimmt

@@ -1,0 +1,313 @@
+// game.cuh — device-side primitives of the 6 nimmt! hot path (sm_100a).
+//
+// Everything here is register-resident integer code: a game is P 128-bit hand words plus a
+// 24-byte row block (include/nimmt_b200.h).  No dynamic register indexing: every
+// data-dependent row / player choice is a predicated select, so nothing spills to local memory
+// and a warp of 32 independent games never diverges inside a placement.
+//
+// Reference semantics: rl_6_nimmt/env.py:64-77,114-172,214-249 (restated in SURVEY.md §3.5).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+// The per-game logic is __host__ __device__ so that tests/host_sim can run the very same code on
+// the CPU against the oracle before GPU time is spent (SURVEY.md §7 hard part 9).  That harness is
+// test-only: libnimmt_b200.so exports no host implementation of any entry point.
+#define NIMMT_HD __host__ __device__ __forceinline__
+
+namespace nimmt {
+
+NIMMT_HD int popc32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+NIMMT_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+NIMMT_HD int imin(int a, int b) { return a < b ? a : b; }
+NIMMT_HD int imax(int a, int b) { return a > b ? a : b; }
+
+constexpr int kRows = 4;
+constexpr int kCards = 104;
+constexpr int kHand = 10;
+constexpr int kMaxPlayers = 10;
+constexpr int kScoreShift = 24;  // score byte = bits 24..31 of hand.w (bits 120..127 of the word)
+
+// SechsNimmtEnv._card_value (env.py:224-239) for cards 0..103.
+#define NIMMT_CARD_VALUES                                                                          \
+    1, 1, 1, 1, 2, 1, 1, 1, 1, 3, 5, 1, 1, 1, 2, 1, 1, 1, 1, 3, 1, 5, 1, 1, 2, 1, 1, 1, 1, 3, 1, 1, \
+    5, 1, 2, 1, 1, 1, 1, 3, 1, 1, 1, 5, 2, 1, 1, 1, 1, 3, 1, 1, 1, 1, 7, 1, 1, 1, 1, 3, 1, 1, 1, 1, \
+    2, 5, 1, 1, 1, 3, 1, 1, 1, 1, 2, 1, 5, 1, 1, 3, 1, 1, 1, 1, 2, 1, 1, 5, 1, 3, 1, 1, 1, 1, 2, 1, \
+    1, 1, 5, 3, 1, 1, 1, 1
+
+__device__ __constant__ uint8_t c_card_value[128] = {NIMMT_CARD_VALUES};
+static const uint8_t h_card_value[128] = {NIMMT_CARD_VALUES};  // host copy (nimmt_card_value, host_sim)
+
+// Copies the 104-entry value table into shared memory (26 words -> 26 distinct banks, so a warp
+// of random lookups is conflict-free).  `smem` must hold 128 bytes.  Call before __syncthreads.
+__device__ __forceinline__ void stage_card_values(uint8_t* smem) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(c_card_value);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) dst[i] = src[i];
+}
+
+// ----------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (Salmon et al. 2011).  Keyed by the caller's seed; the counter is
+// (global game / rollout id, stream, block) so that results never depend on launch geometry.
+// ----------------------------------------------------------------------------------------------
+struct Philox {
+    uint32_t c[4];
+    uint32_t k[2];
+    NIMMT_HD Philox(uint64_t seed, uint64_t id, uint32_t stream, uint32_t block) {
+        c[0] = (uint32_t)id;
+        c[1] = (uint32_t)(id >> 32);
+        c[2] = stream;
+        c[3] = block;
+        k[0] = (uint32_t)seed;
+        k[1] = (uint32_t)(seed >> 32);
+    }
+    // Returns 4 fresh 32-bit words and advances the block counter.
+    NIMMT_HD uint4 next() {
+        uint32_t x0 = c[0], x1 = c[1], x2 = c[2], x3 = c[3], k0 = k[0], k1 = k[1];
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t lo0 = 0xD2511F53u * x0, hi0 = umulhi32(0xD2511F53u, x0);
+            const uint32_t lo1 = 0xCD9E8D57u * x2, hi1 = umulhi32(0xCD9E8D57u, x2);
+            x0 = hi1 ^ x1 ^ k0;
+            x1 = lo1;
+            x2 = hi0 ^ x3 ^ k1;
+            x3 = lo0;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        c[3] += 1;
+        return make_uint4(x0, x1, x2, x3);
+    }
+};
+
+// Uniform integer in [0, n) from 32 random bits by multiply-high.  Bias <= n / 2^32 (< 2.5e-8 for
+// n <= 104): far below any test in this repo can resolve; stated in DESIGN.md §6.
+NIMMT_HD uint32_t below(uint32_t r, uint32_t n) { return umulhi32(r, n); }
+
+// ----------------------------------------------------------------------------------------------
+// 104-bit card sets in a uint4 (x = cards 0..31, y = 32..63, z = 64..95, w bits 0..7 = 96..103).
+// ----------------------------------------------------------------------------------------------
+constexpr uint32_t kHighCardMask = 0xFFu;  // card bits living in .w
+
+NIMMT_HD uint32_t mask_word(const uint4& m, uint32_t word) {
+    uint32_t v = m.x;
+    v = word == 1 ? m.y : v;
+    v = word == 2 ? m.z : v;
+    v = word == 3 ? (m.w & kHighCardMask) : v;
+    return v;
+}
+
+NIMMT_HD bool mask_has(const uint4& m, uint32_t card) {
+    return card < (uint32_t)kCards && ((mask_word(m, card >> 5) >> (card & 31)) & 1u);
+}
+
+NIMMT_HD void mask_clear(uint4& m, uint32_t card) {
+    const uint32_t word = card >> 5, bit = 1u << (card & 31);
+    m.x &= ~(word == 0 ? bit : 0u);
+    m.y &= ~(word == 1 ? bit : 0u);
+    m.z &= ~(word == 2 ? bit : 0u);
+    m.w &= ~(word == 3 ? bit : 0u);
+}
+
+NIMMT_HD void mask_set(uint4& m, uint32_t card) {
+    const uint32_t word = card >> 5, bit = 1u << (card & 31);
+    m.x |= (word == 0 ? bit : 0u);
+    m.y |= (word == 1 ? bit : 0u);
+    m.z |= (word == 2 ? bit : 0u);
+    m.w |= (word == 3 ? bit : 0u);
+}
+
+NIMMT_HD int mask_count(const uint4& m) {
+    return popc32(m.x) + popc32(m.y) + popc32(m.z) + popc32(m.w & kHighCardMask);
+}
+
+// Position of the k-th (0-based) set bit of a non-zero 32-bit word, k < popc(w): 5-level
+// popcount bisection (no __fns: it is a slow emulated loop).
+NIMMT_HD uint32_t select_bit32(uint32_t w, uint32_t k) {
+    uint32_t pos = 0, c;
+    c = popc32(w & 0xFFFFu);
+    if (k >= c) { k -= c; pos = 16; w >>= 16; }
+    c = popc32(w & 0xFFu);
+    if (k >= c) { k -= c; pos += 8; w >>= 8; }
+    c = popc32(w & 0xFu);
+    if (k >= c) { k -= c; pos += 4; w >>= 4; }
+    c = popc32(w & 0x3u);
+    if (k >= c) { k -= c; pos += 2; w >>= 2; }
+    c = w & 1u;
+    if (k >= c) pos += 1;
+    return pos;
+}
+
+// Card id of the k-th smallest card in the set, k < mask_count(m).
+NIMMT_HD uint32_t mask_select(const uint4& m, uint32_t k) {
+    const uint32_t c0 = popc32(m.x), c1 = c0 + popc32(m.y), c2 = c1 + popc32(m.z);
+    uint32_t w = m.x, base = 0, skip = 0;
+    if (k >= c0) { w = m.y; base = 32; skip = c0; }
+    if (k >= c1) { w = m.z; base = 64; skip = c1; }
+    if (k >= c2) { w = m.w & kHighCardMask; base = 96; skip = c2; }
+    return base + select_bit32(w, k - skip);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Board: four rows in registers.
+//   tk[r]    = 4 * top card + r     (the +r makes "largest top below the card" one max and hands
+//                                    back the row index in the low two bits)
+//   meta[r]  = cards in row (bits 0..2) | bull-head sum of the row << 3   (the stored meta byte)
+//   cards[r] = byte i = i-th card of the row (oldest first); unused bytes are 0
+// ----------------------------------------------------------------------------------------------
+struct Board {
+    int tk[kRows];
+    uint32_t meta[kRows];
+    uint64_t cards[kRows];
+
+    // Unpacks the 24-byte row block (three little-endian 64-bit words).
+    NIMMT_HD void unpack(uint64_t q0, uint64_t q1, uint64_t q2) {
+        uint64_t rb[kRows];
+        rb[0] = q0;
+        rb[1] = (q0 >> 48) | (q1 << 16);
+        rb[2] = (q1 >> 32) | (q2 << 32);
+        rb[3] = q2 >> 16;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            cards[r] = rb[r] & 0xFFFFFFFFFFull;
+            meta[r] = (uint32_t)(rb[r] >> 40) & 0xFFu;
+            const uint32_t len = meta[r] & 7u;
+            const uint32_t top = (uint32_t)(cards[r] >> (8u * (len - 1u))) & 0xFFu;
+            tk[r] = (int)(top * 4u) + r;
+        }
+    }
+
+    NIMMT_HD void pack(uint64_t& q0, uint64_t& q1, uint64_t& q2) const {
+        uint64_t rb[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) rb[r] = cards[r] | ((uint64_t)meta[r] << 40);
+        q0 = rb[0] | (rb[1] << 48);
+        q1 = (rb[1] >> 16) | (rb[2] << 32);
+        q2 = (rb[2] >> 32) | (rb[3] << 16);
+    }
+
+    // One placement (env.py:126-134 + _find_row :138-152 + _pick_row_to_replace :154-159 +
+    // _score_row :161-172).  Returns the bull heads taken (0 if none).
+    //   undercut (card below every top)   -> row with the smallest bull-head sum, lowest index on
+    //                                        ties; the player takes the whole old row
+    //   otherwise                         -> row with the largest top below the card; if it
+    //                                        already holds five cards the player takes those five
+    // In both take cases the penalty is the row's sum BEFORE the append and the row restarts with
+    // the played card alone.
+    NIMMT_HD int place(int card, int value) {
+        const int c4 = card * 4;
+        const int n0 = tk[0] < c4 ? tk[0] : -1, n1 = tk[1] < c4 ? tk[1] : -1;
+        const int n2 = tk[2] < c4 ? tk[2] : -1, n3 = tk[3] < c4 ? tk[3] : -1;
+        const int best = imax(imax(n0, n1), imax(n2, n3));
+        const bool under = best < 0;
+        // argmin over (sum, row): meta >> 3 is the sum; low bits carry the row index
+        const int u0 = (int)((meta[0] >> 3) << 2), u1 = (int)((meta[1] >> 3) << 2) | 1;
+        const int u2 = (int)((meta[2] >> 3) << 2) | 2, u3 = (int)((meta[3] >> 3) << 2) | 3;
+        const int cheapest = imin(imin(u0, u1), imin(u2, u3));
+        const int r = (under ? cheapest : best) & 3;
+        const bool is0 = r == 0, is1 = r == 1, is2 = r == 2;
+        const uint32_t m = is0 ? meta[0] : is1 ? meta[1] : is2 ? meta[2] : meta[3];
+        const uint64_t cr = is0 ? cards[0] : is1 ? cards[1] : is2 ? cards[2] : cards[3];
+        const uint32_t len = m & 7u, sum = m >> 3;
+        const bool take = under || len == 5u;
+        const int penalty = take ? (int)sum : 0;
+        const uint32_t keep_len = take ? 0u : len;
+        const uint32_t new_meta = (keep_len + 1u) | (((take ? 0u : sum) + (uint32_t)value) << 3);
+        const uint64_t new_cards = (take ? 0ull : cr) | ((uint64_t)(uint32_t)card << (8u * keep_len));
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+            const bool hit = r == i;
+            tk[i] = hit ? c4 + i : tk[i];
+            meta[i] = hit ? new_meta : meta[i];
+            cards[i] = hit ? new_cards : cards[i];
+        }
+        return penalty;
+    }
+};
+
+// ----------------------------------------------------------------------------------------------
+// Sorting network for the (card << 4 | player) keys of one step (env.py:124-125).  Optimal-size
+// networks for n <= 10 (Knuth TAOCP 3, 5.3.4); fully unrolled compare-exchange on registers.
+// ----------------------------------------------------------------------------------------------
+NIMMT_HD void cswap(int& a, int& b) {
+    const int lo = imin(a, b), hi = imax(a, b);
+    a = lo;
+    b = hi;
+}
+
+template <int N>
+NIMMT_HD void sort_keys(int (&k)[N]) {
+#define CS(i, j) cswap(k[i], k[j])
+    if constexpr (N == 2) {
+        CS(0, 1);
+    } else if constexpr (N == 3) {
+        CS(0, 2); CS(0, 1); CS(1, 2);
+    } else if constexpr (N == 4) {
+        CS(0, 2); CS(1, 3); CS(0, 1); CS(2, 3); CS(1, 2);
+    } else if constexpr (N == 5) {
+        CS(0, 3); CS(1, 4); CS(0, 2); CS(1, 3); CS(0, 1); CS(2, 4); CS(1, 2); CS(3, 4); CS(2, 3);
+    } else if constexpr (N == 6) {
+        CS(0, 5); CS(1, 3); CS(2, 4); CS(1, 2); CS(3, 4); CS(0, 3); CS(2, 5); CS(0, 1); CS(2, 3);
+        CS(4, 5); CS(1, 2); CS(3, 4);
+    } else if constexpr (N == 7) {
+        CS(0, 6); CS(2, 3); CS(4, 5); CS(0, 2); CS(1, 4); CS(3, 6); CS(0, 1); CS(2, 5); CS(3, 4);
+        CS(1, 2); CS(4, 6); CS(2, 3); CS(4, 5); CS(1, 2); CS(3, 4); CS(5, 6);
+    } else if constexpr (N == 8) {
+        CS(0, 2); CS(1, 3); CS(4, 6); CS(5, 7); CS(0, 4); CS(1, 5); CS(2, 6); CS(3, 7); CS(0, 1);
+        CS(2, 3); CS(4, 5); CS(6, 7); CS(2, 4); CS(3, 5); CS(1, 4); CS(3, 6); CS(1, 2); CS(3, 4);
+        CS(5, 6);
+    } else if constexpr (N == 9) {
+        CS(0, 3); CS(1, 7); CS(2, 5); CS(4, 8); CS(0, 7); CS(2, 4); CS(3, 8); CS(5, 6); CS(0, 2);
+        CS(1, 3); CS(4, 5); CS(7, 8); CS(1, 4); CS(3, 6); CS(5, 7); CS(0, 1); CS(2, 4); CS(3, 5);
+        CS(6, 8); CS(2, 3); CS(4, 5); CS(6, 7); CS(1, 2); CS(3, 4); CS(5, 6);
+    } else if constexpr (N == 10) {
+        CS(0, 8); CS(1, 9); CS(2, 7); CS(3, 5); CS(4, 6); CS(0, 2); CS(1, 4); CS(5, 8); CS(7, 9);
+        CS(0, 3); CS(2, 4); CS(5, 7); CS(6, 9); CS(0, 1); CS(3, 6); CS(8, 9); CS(1, 5); CS(2, 3);
+        CS(4, 8); CS(6, 7); CS(1, 2); CS(3, 5); CS(4, 6); CS(7, 8); CS(2, 3); CS(4, 5); CS(6, 7);
+        CS(3, 4); CS(5, 6);
+    }
+#undef CS
+}
+
+// ----------------------------------------------------------------------------------------------
+// Packed-state addressing (SoA planes, include/nimmt_b200.h).
+// ----------------------------------------------------------------------------------------------
+struct StateView {
+    uint4* hand;    // [P][B]
+    uint4* rows_a;  // [B]
+    uint2* rows_b;  // [B]
+    int64_t B;
+    __host__ __device__ StateView(void* base, int64_t num_games, int num_players) : B(num_games) {
+        hand = reinterpret_cast<uint4*>(base);
+        rows_a = hand + (int64_t)num_players * num_games;
+        rows_b = reinterpret_cast<uint2*>(rows_a + num_games);
+    }
+};
+
+NIMMT_HD void load_rows(const StateView& s, int64_t g, Board& b) {
+    const uint4 a = s.rows_a[g];
+    const uint2 c = s.rows_b[g];
+    b.unpack((uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
+             (uint64_t)c.x | ((uint64_t)c.y << 32));
+}
+
+NIMMT_HD void store_rows(const StateView& s, int64_t g, const Board& b) {
+    uint64_t q0, q1, q2;
+    b.pack(q0, q1, q2);
+    s.rows_a[g] = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32));
+    s.rows_b[g] = make_uint2((uint32_t)q2, (uint32_t)(q2 >> 32));
+}
+
+}  // namespace nimmt

@@ -1,0 +1,97 @@
+// mcs_kernels.cu — Monte-Carlo search rollouts (BaseMCAgent._mcts, agents/mcts.py:91-154) for
+// batches of decisions.  Integer-issue bound: the root (64 B) is read once per block, a rollout
+// lives entirely in registers, and each block leaves three 64-bit atomics behind.
+#include "abi_common.cuh"
+#include "rollout.cuh"
+
+namespace nimmt {
+
+constexpr int kMcsThreads = 256;
+
+static_assert(sizeof(nimmt_root) == 64, "nimmt_root must be 64 bytes");
+
+// grid = (chunks, 10 candidate ranks, D roots).  Block (c, a, d) runs local rollouts
+// [c * kMcsThreads * iters, (c + 1) * kMcsThreads * iters) of candidate a of root d; local rollout
+// i is global rollout j = rank + i * world, and the RNG is keyed by (d, a, j) only.
+template <int P>
+__global__ void __launch_bounds__(kMcsThreads)
+k_mcs_rollouts(const nimmt_root* __restrict__ roots, int64_t local_rollouts, int iters, uint64_t seed, int rank, int world,
+               unsigned long long* __restrict__ stats) {
+    __shared__ uint8_t values[128];
+    __shared__ nimmt_root root;
+    __shared__ long long red[3][kMcsThreads / 32];
+    stage_card_values(values);
+    const int d = blockIdx.z, a = blockIdx.y;
+    if (threadIdx.x < 16) reinterpret_cast<uint32_t*>(&root)[threadIdx.x] = reinterpret_cast<const uint32_t*>(roots + d)[threadIdx.x];
+    __syncthreads();
+
+    uint4 own, pool;
+    BoardLite board;
+    if (!decode_root<P>(root, values, own, pool, board)) return;  // whole block; stats stay zero
+    if (a >= mask_count(own)) return;
+    const int first = (int)mask_select(own, (uint32_t)a);
+
+    long long s = 0, ss = 0, cnt = 0;
+    const int64_t base = ((int64_t)blockIdx.x * iters) * kMcsThreads + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+        const int64_t i = base + (int64_t)it * kMcsThreads;
+        if (i < local_rollouts) {
+            const uint64_t j = (uint64_t)rank + (uint64_t)i * (uint64_t)world;
+            const uint64_t id = ((uint64_t)d << 44) | ((uint64_t)a << 40) | j;
+            const int out = rollout<P>(own, pool, board, first, values, seed, id);
+            s += out; ss += (long long)out * out; cnt += 1;
+        }
+    }
+    // warp reduce, then one atomic triple per block
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_down_sync(0xFFFFFFFFu, s, off);
+        ss += __shfl_down_sync(0xFFFFFFFFu, ss, off);
+        cnt += __shfl_down_sync(0xFFFFFFFFu, cnt, off);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; red[2][warp] = cnt; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        long long t = 0;
+#pragma unroll
+        for (int w = 0; w < kMcsThreads / 32; ++w) t += red[threadIdx.x][w];
+        if (t != 0) atomicAdd(stats + ((int64_t)d * 10 + a) * 3 + threadIdx.x, (unsigned long long)t);
+    }
+}
+
+}  // namespace nimmt
+
+using namespace nimmt;
+
+extern "C" {
+
+int nimmt_mcs_rollouts(const nimmt_root* roots, int num_roots, int num_players, int64_t rollouts_per_action, uint64_t seed,
+                       int rank, int world, int64_t* stats, void* stream) {
+    if (!roots || !stats || num_roots < 0 || num_roots > 65535 || rollouts_per_action < 0 || world < 1 || rank < 0 ||
+        rank >= world || num_players < 1 || num_players > kMaxPlayers)
+        return NIMMT_E_BADARG;
+    if (rollouts_per_action >= ((int64_t)1 << 40)) return NIMMT_E_BADARG;
+    if ((reinterpret_cast<uintptr_t>(roots) & 15u) || (reinterpret_cast<uintptr_t>(stats) & 7u)) return NIMMT_E_ALIGN;
+    const int64_t local = rollouts_per_action > rank ? (rollouts_per_action - rank + world - 1) / world : 0;
+    if (num_roots == 0 || local == 0) return NIMMT_OK;
+    // rollouts per thread: enough blocks to fill 148 SMs several times over, few enough atomics
+    const int64_t total_threads = local * 10 * (int64_t)num_roots;
+    int iters = (int)(total_threads / ((int64_t)kMcsThreads * 148 * 32));
+    iters = iters < 1 ? 1 : iters > 64 ? 64 : iters;
+    const int64_t per_block = (int64_t)kMcsThreads * iters;
+    const int64_t chunks = (local + per_block - 1) / per_block;
+    if (chunks > 0x7FFFFFFF) return NIMMT_E_BADARG;
+    dim3 grid((unsigned)chunks, 10, (unsigned)num_roots);
+    unsigned long long* st = reinterpret_cast<unsigned long long*>(stats);
+    cudaStream_t cs = (cudaStream_t)stream;
+    switch (num_players) {
+#define CASE(P_) case P_: k_mcs_rollouts<P_><<<grid, kMcsThreads, 0, cs>>>(roots, local, iters, seed, rank, world, st); break;
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
+#undef CASE
+        default: return NIMMT_E_BADARG;
+    }
+    return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+"""6 nimmt! environments backed by the sm_100a kernels.
+
+Two front ends over the same packed device state (include/nimmt_b200.h):
+
+* :class:`BatchedSechsNimmtEnv` — B independent games stepped in lock-step on the GPU.  This is
+  the throughput path (BASELINE.json configs 2 and 5).
+* :class:`SechsNimmtEnv` — a drop-in for the reference class of the same name
+  (``rl_6_nimmt/env.py:13``): identical constructor, ``reset / reset_to / step / render /
+  _create_states``, identical return structure (lists of int64[47] arrays + legal-card lists,
+  int32 rewards, Python bool done, ``{}``), identical exceptions.  It is a B = 1 view of the
+  batched engine; every rule is evaluated on the device.
+
+There is no CPU implementation of the rules in this package.
+"""
+import logging
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+logger = logging.getLogger(__name__)
+
+NUM_ROWS, NUM_CARDS, THRESHOLD, HAND_SIZE = 4, 104, 6, 10
+
+_TORCH_DT = {torch.int8: N.DT_I8, torch.int16: N.DT_I16, torch.float32: N.DT_F32, torch.int64: N.DT_I64}
+
+
+class InvalidMoveException(Exception):
+    """Same name and meaning as rl_6_nimmt/env.py:9-10."""
+
+
+class Discrete:
+    """Duck-typed gym.spaces.Discrete (gym is not a dependency; only ``.n`` is read, agents/base.py:19)."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __repr__(self):
+        return f"Discrete({self.n})"
+
+
+class Box:
+    """Duck-typed gym.spaces.Box (only ``.shape`` is read, agents/base.py:18)."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+    def __repr__(self):
+        return f"Box({self.low}, {self.high}, {self.shape}, {self.dtype})"
+
+
+def _as_device(x, dtype, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device)
+
+
+class BatchedSechsNimmtEnv:
+    """B games of ``num_players`` players on one GPU.
+
+    All methods enqueue work on the current CUDA stream and return device tensors; nothing
+    synchronises unless stated.  ``seed`` keys the counter-based RNG used by :meth:`reset` and
+    :meth:`random_actions`; ``game0`` is the global index of game 0, so a batch split over several
+    GPUs deals exactly the games the unsplit batch would.
+    """
+
+    def __init__(self, num_games, num_players, include_summaries=True, device=None, seed=0, game0=0):
+        assert num_players > 0                                      # env.py:19
+        assert NUM_CARDS >= 10 * num_players + NUM_ROWS            # env.py:21
+        assert num_games >= 0
+        if not torch.cuda.is_available():
+            raise N.NimmtNativeError("BatchedSechsNimmtEnv needs a CUDA device; there is no CPU fallback")
+        self.lib = N.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.num_games, self.num_players = int(num_games), int(num_players)
+        self.include_summaries = bool(include_summaries)
+        self.obs_len = self.lib.nimmt_obs_len(int(self.include_summaries))
+        self.seed, self.game0 = int(seed), int(game0)
+        self.episode = 0   # bumped by reset(): later deals differ from earlier ones
+        self.turn = 0
+        B, P = self.num_games, self.num_players
+        with torch.cuda.device(self.device):
+            self.state = torch.zeros(max(self.lib.nimmt_state_bytes(B, P), 16), dtype=torch.uint8, device=self.device)
+            self.rewards = torch.zeros((B, P), dtype=torch.int8, device=self.device)
+            self.done = torch.zeros((B,), dtype=torch.uint8, device=self.device)
+            self.illegal = torch.zeros((B,), dtype=torch.uint8, device=self.device)
+            self._actions = torch.zeros((B, P), dtype=torch.uint8, device=self.device)
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _deal_seed(self):
+        return (self.seed + 0x9E3779B97F4A7C15 * self.episode) & 0xFFFFFFFFFFFFFFFF
+
+    # -- reference API, batched ----------------------------------------------------------------
+    def reset(self, seed=None):
+        """SechsNimmtEnv.reset (env.py:43-51) for every game; device RNG."""
+        if seed is not None:
+            self.seed, self.episode = int(seed), 0
+        with torch.cuda.device(self.device):
+            N.check(self.lib.nimmt_deal(N.ptr(self.state), self.num_games, self.num_players, self._deal_seed(),
+                                        self.game0, self._stream()), "nimmt_deal")
+        self.episode += 1
+        self.turn = 0
+        return self
+
+    def reset_from_perm(self, perm):
+        """_deal from caller-supplied shuffled decks, uint8 [B,104] (env.py:103-112)."""
+        perm = _as_device(perm, torch.uint8, self.device)
+        assert perm.shape == (self.num_games, NUM_CARDS)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.nimmt_deal_from_perm(N.ptr(self.state), N.ptr(perm), self.num_games, self.num_players,
+                                                  self._stream()), "nimmt_deal_from_perm")
+        self.turn = 0
+        return self
+
+    def reset_to(self, board, hands, check=True):
+        """SechsNimmtEnv.reset_to (env.py:53-62): board int8 [B,4,6], hands int8 [B,P,10], -1 padded."""
+        board = _as_device(board, torch.int8, self.device)
+        hands = _as_device(hands, torch.int8, self.device)
+        assert board.shape == (self.num_games, NUM_ROWS, THRESHOLD), board.shape
+        assert hands.shape == (self.num_games, self.num_players, HAND_SIZE), hands.shape
+        invalid = torch.zeros((self.num_games,), dtype=torch.uint8, device=self.device) if check else None
+        with torch.cuda.device(self.device):
+            N.check(self.lib.nimmt_reset_to(N.ptr(self.state), N.ptr(board), N.ptr(hands), N.ptr(invalid), self.num_games,
+                                            self.num_players, self._stream()), "nimmt_reset_to")
+        if check and bool(invalid.any()):
+            bad = int(torch.nonzero(invalid)[0])
+            raise ValueError(f"reset_to: malformed board/hands for game {bad} (empty or over-long row, bad or duplicate card)")
+        self.turn = 0
+        return self
+
+    def step(self, actions, check=False):
+        """SechsNimmtEnv.step (env.py:64-77) without the observation rebuild.
+
+        actions: uint8 [B,P] device tensor.  Returns (rewards int8 [B,P], done uint8 [B]) — views of
+        buffers owned by the env, overwritten by the next step.  ``self.illegal`` flags games whose
+        move was rejected (left untouched, env.py:68-69); with ``check=True`` the call synchronises
+        and raises InvalidMoveException if any game was flagged.
+        """
+        assert actions.shape == (self.num_games, self.num_players) and actions.dtype == torch.uint8 and actions.is_cuda
+        actions = actions.contiguous()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.nimmt_step(N.ptr(self.state), N.ptr(actions), N.ptr(self.rewards), N.ptr(self.done),
+                                        N.ptr(self.illegal), self.num_games, self.num_players, self._stream()), "nimmt_step")
+        self.turn += 1
+        if check and bool(self.illegal.any()):
+            bad = int(torch.nonzero(self.illegal)[0])
+            raise InvalidMoveException(f"game {bad}: a played card is not in its owner's hand")
+        return self.rewards, self.done
+
+    def random_actions(self, out=None, turn=None):
+        """DrunkHamster for every seat (agents/random.py:8-10): uint8 [B,P]."""
+        out = self._actions if out is None else out
+        with torch.cuda.device(self.device):
+            N.check(self.lib.nimmt_random_actions(N.ptr(self.state), N.ptr(out), self.num_games, self.num_players,
+                                                  self._deal_seed(), self.turn if turn is None else int(turn), self.game0,
+                                                  self._stream()), "nimmt_random_actions")
+        return out
+
+    def step_random(self, record_actions=False):
+        """random_actions + step fused in one kernel (random-vs-random play)."""
+        acts = self._actions if record_actions else None
+        with torch.cuda.device(self.device):
+            N.check(self.lib.nimmt_step_random(N.ptr(self.state), N.ptr(acts), N.ptr(self.rewards), N.ptr(self.done),
+                                               self.num_games, self.num_players, self._deal_seed(), self.turn, self.game0,
+                                               self._stream()), "nimmt_step_random")
+        self.turn += 1
+        return self.rewards, self.done
+
+    def observe(self, dtype=torch.float32, out=None, n_legal=None):
+        """SechsNimmtEnv._create_states (env.py:174-212): [B,P,L] tensor, L = 47 (35 without summaries).
+
+        Legal actions of seat p in game b are the non-negative entries of obs[b,p,:10].
+        """
+        B, P, L = self.num_games, self.num_players, self.obs_len
+        if out is None:
+            out = torch.empty((B, P, L), dtype=dtype, device=self.device)
+        assert out.shape == (B, P, L) and out.is_contiguous()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.nimmt_observe(N.ptr(self.state), N.ptr(out), N.ptr(n_legal), B, P, int(self.include_summaries),
+                                           _TORCH_DT[out.dtype], self._stream()), "nimmt_observe")
+        return out
+
+    def scores(self, out=None):
+        """Cumulative Hornochsen per seat (env.py:32,167): uint8 [B,P]."""
+        if out is None:
+            out = torch.empty((self.num_games, self.num_players), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.nimmt_scores(N.ptr(self.state), N.ptr(out), self.num_games, self.num_players, self._stream()),
+                    "nimmt_scores")
+        return out
+
+
+class SechsNimmtEnv:
+    """Drop-in for ``rl_6_nimmt.env.SechsNimmtEnv`` (env.py:13-256), rules evaluated on the GPU.
+
+    ``reset()`` shuffles with ``np.random`` exactly as the reference does (env.py:103-104), so a
+    program that seeds NumPy sees the same deals from both implementations.
+    """
+
+    metadata = {"render.modes": ["human"]}
+
+    def __init__(self, num_players, num_rows=4, num_cards=104, threshold=6, include_summaries=True, player_names=None,
+                 verbose=True, device=None):
+        assert num_players > 0
+        assert num_rows > 0
+        assert num_cards >= 10 * num_players + num_rows
+        if (num_rows, num_cards, threshold) != (NUM_ROWS, NUM_CARDS, THRESHOLD):
+            raise NotImplementedError("the CUDA kernels are built for num_rows=4, num_cards=104, threshold=6 "
+                                      "(the only values the reference's callers use)")
+        self._num_players, self._num_rows, self._num_cards, self._threshold = num_players, num_rows, num_cards, threshold
+        self._include_summaries = include_summaries
+        self._player_names = player_names
+        self.action_space = Discrete(num_cards)
+        self.reward_range = (-float("inf"), 0)
+        state_shape = (10 + 1 + int(include_summaries) * 3 * num_rows + num_rows * threshold,)
+        self.observation_space = Box(low=-1.0, high=2.0, shape=state_shape, dtype=np.float32)
+        self.spec = None
+        self.verbose = verbose
+        self._engine = None
+        self._device = device
+        self._cache = None  # (obs int64 [P,L] numpy, scores int32 [P]) of the current state
+
+    # engine is created lazily: agents/base.py:11-12 builds a throw-away env just to read the spaces
+    def _eng(self):
+        if self._engine is None:
+            self._engine = BatchedSechsNimmtEnv(1, self._num_players, self._include_summaries, device=self._device)
+            board = -np.ones((1, NUM_ROWS, THRESHOLD), np.int8)
+            board[0, :, 0] = np.arange(NUM_ROWS)  # placeholder position until reset()/reset_to()
+            self._engine.reset_to(board, -np.ones((1, self._num_players, HAND_SIZE), np.int8), check=False)
+        return self._engine
+
+    def _sync_cache(self):
+        if self._cache is None:
+            eng = self._eng()
+            obs = eng.observe(dtype=torch.int64)[0].cpu().numpy()
+            scores = eng.scores()[0].cpu().numpy().astype(np.int32)
+            self._cache = (obs, scores)
+        return self._cache
+
+    # -- reference API -----------------------------------------------------------------------------
+    def reset(self):
+        cards = np.arange(0, self._num_cards, 1, dtype=np.int32)
+        np.random.shuffle(cards)  # same RNG call as env.py:103-104
+        if self.verbose:
+            logger.debug("Dealing cards")
+        self._eng().reset_from_perm(cards.astype(np.uint8)[None])
+        self._cache = None
+        return self._create_states()
+
+    def reset_to(self, board, hands):
+        assert len(board) == self._num_rows and len(hands) == self._num_players
+        b = -np.ones((1, NUM_ROWS, THRESHOLD), np.int8)
+        for r, cards in enumerate(board):
+            b[0, r, : len(cards)] = cards
+        h = -np.ones((1, self._num_players, HAND_SIZE), np.int8)
+        for p, cards in enumerate(hands):
+            h[0, p, : len(cards)] = sorted(int(c) for c in cards)
+        self._eng().reset_to(b, h)
+        self._cache = None
+        return self._create_states()
+
+    def step(self, action):
+        assert len(action) == self._num_players                     # env.py:67
+        eng = self._eng()
+        cards = [int(c) for c in action]
+        acts = torch.tensor([[c if 0 <= c < 256 else 255 for c in cards]], dtype=torch.uint8).to(eng.device)
+        rewards, done = eng.step(acts)
+        packed = torch.cat([rewards.view(torch.uint8).flatten(), done, eng.illegal]).cpu().numpy()
+        P = self._num_players
+        if packed[P + 1]:
+            # the device rejected the step and left the game untouched (env.py:68-69, 117-118)
+            hands = self._hands
+            for player, card in enumerate(cards):
+                if card not in hands[player]:
+                    raise InvalidMoveException(f"Player {player + 1} tried to play card {card + 1}, but their hand is {hands[player]}")
+            raise InvalidMoveException("illegal move")  # unreachable: device and host views agree
+        self._cache = None
+        if self.verbose and logger.isEnabledFor(logging.DEBUG):
+            for card, player in sorted((c, p) for p, c in enumerate(cards)):
+                logger.debug(f"{self._player_name(player)} plays card {card + 1}")
+        states = self._create_states()
+        return states, packed[:P].view(np.int8).astype(np.int32), bool(packed[P]), dict()
+
+    def _create_states(self):
+        obs, _ = self._sync_cache()
+        player_states = [obs[p].copy() for p in range(self._num_players)]
+        legal_actions = [[int(c) for c in obs[p, :HAND_SIZE] if c >= 0] for p in range(self._num_players)]
+        return player_states, legal_actions
+
+    # -- the attributes tests and probes poke at (env.py:30-32) -------------------------------------
+    @property
+    def _board(self):
+        obs, _ = self._sync_cache()
+        grid = obs[0, -NUM_ROWS * THRESHOLD:].reshape(NUM_ROWS, THRESHOLD)
+        return [[int(c) for c in row if c >= 0] for row in grid]
+
+    @property
+    def _hands(self):
+        obs, _ = self._sync_cache()
+        return [[int(c) for c in obs[p, :HAND_SIZE] if c >= 0] for p in range(self._num_players)]
+
+    @property
+    def _scores(self):
+        return self._sync_cache()[1].copy()
+
+    def _is_done(self):
+        return len(self._hands[0]) == 0
+
+    @staticmethod
+    def _card_value(card):
+        assert 0 <= card < NUM_CARDS
+        return N.lib().nimmt_card_value(int(card))
+
+    # -- host-only presentation (env.py:79-97, 241-256) ----------------------------------------------
+    def _format_card(self, card):
+        marks = {1: " ", 2: ".", 3: ":", 5: "+", 7: "#"}
+        return f"{card + 1:>3d}{marks[self._card_value(card)]}"
+
+    def _player_name(self, player):
+        if self._player_names is None:
+            return f"Player {player + 1:d}"
+        width = max(len(name) for name in self._player_names)
+        return f"{self._player_names[player]:<{width}} (player {player + 1:d})"
+
+    def render(self, mode="human"):
+        rule = "-" * 120
+        logger.info(rule)
+        logger.info("Board:")
+        for cards in self._board:
+            shown = " ".join(self._format_card(c) for c in cards)
+            logger.info("  " + shown + "   _ " * (self._threshold - len(cards) - 1) + "   * ")
+        logger.info("Players:")
+        scores, hands = self._scores, self._hands
+        for player in range(self._num_players):
+            held = "no cards " if not hands[player] else "cards " + " ".join(self._format_card(c) for c in hands[player])
+            logger.info(f"  {self._player_name(player)}: {scores[player]:>3d} Hornochsen, " + held)
+        if self._is_done():
+            winner, loser = int(np.argmin(scores)), int(np.argmax(scores))
+            logger.info(f"The game is over! {self._player_name(winner)} wins, {self._player_name(loser)} loses. Congratulations!")
+        logger.info(rule)

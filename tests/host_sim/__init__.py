@@ -1,0 +1,69 @@
+"""ctypes binding of the TEST-ONLY host build of the product's per-game logic (host_sim.cu)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libhost_sim.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(_HERE, "host_sim.cu")
+        csrc = os.path.join(_HERE, "..", "..", "rl-6-nimmt_b200", "csrc")
+        newest = max(os.path.getmtime(p) for p in [src] + [os.path.join(csrc, f) for f in ("game.cuh", "step.cuh", "rollout.cuh")])
+        if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
+            subprocess.check_call(["nvcc", "-O1", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+                                   "-Wno-deprecated-gpu-targets", "-o", _LIB, src])
+        _lib = ctypes.CDLL(_LIB)
+        _lib.sim_select.restype = ctypes.c_uint
+        _lib.sim_select.argtypes = [ctypes.c_uint32] * 5
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def replay(P, rows0, hands0, actions):
+    rows0 = np.ascontiguousarray(rows0, np.int8)
+    hands0 = np.ascontiguousarray(hands0, np.int8)
+    actions = np.ascontiguousarray(actions, np.int8)
+    n, T = actions.shape[:2]
+    out = dict(rewards=np.zeros((n, T, P), np.int8), done=np.zeros((n, T), np.uint8), illegal=np.zeros((n, T), np.uint8),
+               hands=np.zeros((n, T, P, 10), np.int8), boards=np.zeros((n, T, 4, 6), np.int8), scores=np.zeros((n, T, P), np.int16))
+    rc = lib().sim_replay(P, n, T, _p(rows0), _p(hands0), _p(actions), _p(out["rewards"]), _p(out["done"]), _p(out["illegal"]),
+                          _p(out["hands"]), _p(out["boards"]), _p(out["scores"]))
+    assert rc == 0
+    return out
+
+
+def deal(P, n, seed, game0=0):
+    hands = np.zeros((n, P, 10), np.int8)
+    boards = np.zeros((n, 4, 6), np.int8)
+    rc = lib().sim_deal(P, n, ctypes.c_uint64(seed), ctypes.c_uint64(game0), _p(hands), _p(boards))
+    assert rc == 0
+    return hands, boards
+
+
+def random_actions(P, rows0, hands0, seed, turn, game0=0):
+    rows0 = np.ascontiguousarray(rows0, np.int8)
+    hands0 = np.ascontiguousarray(hands0, np.int8)
+    n = len(rows0)
+    act = np.zeros((n, P), np.uint8)
+    rc = lib().sim_random_actions(P, n, _p(rows0), _p(hands0), ctypes.c_uint64(seed), ctypes.c_uint64(game0), ctypes.c_uint32(turn), _p(act))
+    assert rc == 0
+    return act
+
+
+def mcs(P, root_bytes, rollouts, seed, rank=0, world=1):
+    """root_bytes: 64-byte nimmt_root image. Returns int64 [10,3] (sum, sumsq, count) per first-card rank."""
+    buf = (ctypes.c_uint8 * 64).from_buffer_copy(root_bytes)
+    stats = np.zeros((10, 3), np.int64)
+    rc = lib().sim_mcs(P, buf, ctypes.c_int64(rollouts), ctypes.c_uint64(seed), rank, world, _p(stats))
+    assert rc == 0, rc
+    return stats

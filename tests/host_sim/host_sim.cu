@@ -1,0 +1,165 @@
+// host_sim.cu — TEST-ONLY harness: runs the product's __host__ __device__ per-game logic
+// (rl-6-nimmt_b200/csrc/game.cuh, step.cuh) on the CPU so that tests can diff it against the
+// oracle without a GPU.  It is never linked into libnimmt_b200.so and never used as a fallback.
+#include <cstdint>
+#include <cstring>
+
+#include "../../rl-6-nimmt_b200/csrc/rollout.cuh"
+#include "../../rl-6-nimmt_b200/csrc/step.cuh"
+
+using namespace nimmt;
+
+template <int P>
+static void unpack_to_arrays(const Game<P>& g, int8_t* hands /*[P][10]*/, int8_t* board /*[4][6]*/, int16_t* scores) {
+    for (int p = 0; p < P; ++p) {
+        int n = 0;
+        for (int c = 0; c < kCards; ++c)
+            if (mask_has(g.hand[p], c)) hands[p * 10 + n++] = (int8_t)c;
+        for (; n < 10; ++n) hands[p * 10 + n] = -1;
+        scores[p] = (int16_t)(g.hand[p].w >> kScoreShift);
+    }
+    // go through pack/unpack so the stored representation is what gets checked
+    uint64_t q0, q1, q2;
+    g.board.pack(q0, q1, q2);
+    Board b;
+    b.unpack(q0, q1, q2);
+    for (int r = 0; r < kRows; ++r) {
+        const int len = b.meta[r] & 7;
+        for (int i = 0; i < 6; ++i) board[r * 6 + i] = i < len ? (int8_t)((b.cards[r] >> (8 * i)) & 0xFF) : -1;
+    }
+}
+
+template <int P>
+static void init_game(Game<P>& g, const int8_t* rows0 /*[4][6]*/, const int8_t* hands0 /*[P][10]*/) {
+    for (int r = 0; r < kRows; ++r) {
+        uint64_t cards = 0;
+        uint32_t len = 0, sum = 0, top = 0;
+        for (int i = 0; i < 6 && rows0[r * 6 + i] >= 0; ++i) {
+            const uint32_t c = rows0[r * 6 + i];
+            cards |= (uint64_t)c << (8 * len);
+            ++len; sum += h_card_value[c]; top = c;
+        }
+        g.board.cards[r] = cards;
+        g.board.meta[r] = len | (sum << 3);
+        g.board.tk[r] = top * 4 + r;
+    }
+    for (int p = 0; p < P; ++p) {
+        g.hand[p] = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 10; ++i)
+            if (hands0[p * 10 + i] >= 0) mask_set(g.hand[p], hands0[p * 10 + i]);
+    }
+}
+
+template <int P>
+static void replay(int n, int turns, const int8_t* rows0, const int8_t* hands0, const int8_t* actions, int8_t* rewards,
+                   uint8_t* done, uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores) {
+    for (int gi = 0; gi < n; ++gi) {
+        Game<P> g;
+        init_game<P>(g, rows0 + gi * 24, hands0 + gi * P * 10);
+        for (int t = 0; t < turns; ++t) {
+            const size_t gt = (size_t)gi * turns + t;
+            int act[P], pen[P];
+            for (int p = 0; p < P; ++p) act[p] = (uint8_t)actions[gt * P + p];
+            const bool legal = step_game<P>(g, act, h_card_value, pen);
+            illegal[gt] = !legal;
+            done[gt] = game_done<P>(g);
+            for (int p = 0; p < P; ++p) rewards[gt * P + p] = (int8_t)(-pen[p]);
+            unpack_to_arrays<P>(g, hands + gt * P * 10, boards + gt * 24, scores + gt * P);
+        }
+    }
+}
+
+template <int P>
+static void deal(int n, uint64_t seed, uint64_t game0, int8_t* hands, int8_t* boards) {
+    int16_t sc[P];
+    for (int gi = 0; gi < n; ++gi) {
+        Game<P> g;
+        deal_game<P>(g, seed, game0 + gi, h_card_value);
+        unpack_to_arrays<P>(g, hands + (size_t)gi * P * 10, boards + (size_t)gi * 24, sc);
+    }
+}
+
+template <int P>
+static void rand_act(int n, const int8_t* rows0, const int8_t* hands0, uint64_t seed, uint64_t game0, uint32_t turn, uint8_t* actions) {
+    for (int gi = 0; gi < n; ++gi) {
+        Game<P> g;
+        init_game<P>(g, rows0 + gi * 24, hands0 + gi * P * 10);
+        int act[P];
+        random_actions_game<P>(g, seed, game0 + gi, turn, act);
+        for (int p = 0; p < P; ++p) actions[(size_t)gi * P + p] = (uint8_t)act[p];
+    }
+}
+
+#define DISPATCH(P_, CALL)                                  \
+    switch (P_) {                                           \
+        case 1: { constexpr int P = 1; CALL; } break;       \
+        case 2: { constexpr int P = 2; CALL; } break;       \
+        case 3: { constexpr int P = 3; CALL; } break;       \
+        case 4: { constexpr int P = 4; CALL; } break;       \
+        case 5: { constexpr int P = 5; CALL; } break;       \
+        case 6: { constexpr int P = 6; CALL; } break;       \
+        case 7: { constexpr int P = 7; CALL; } break;       \
+        case 8: { constexpr int P = 8; CALL; } break;       \
+        case 9: { constexpr int P = 9; CALL; } break;       \
+        case 10: { constexpr int P = 10; CALL; } break;     \
+        default: return -1;                                 \
+    }
+
+template <int N>
+static int check_network() {
+    // 0-1 principle: a comparator network sorts everything iff it sorts all 2^N bit vectors
+    for (unsigned m = 0; m < (1u << N); ++m) {
+        int k[N];
+        for (int i = 0; i < N; ++i) k[i] = (m >> i) & 1;
+        sort_keys<N>(k);
+        for (int i = 1; i < N; ++i)
+            if (k[i - 1] > k[i]) return N;
+    }
+    return 0;
+}
+
+template <int P>
+static int mcs(const nimmt_root& root, int64_t R, uint64_t seed, int rank, int world, int64_t* stats) {
+    uint4 own, pool;
+    BoardLite board;
+    if (!decode_root<P>(root, h_card_value, own, pool, board)) return -2;
+    const int n = mask_count(own);
+    for (int a = 0; a < n; ++a) {
+        const int first = (int)mask_select(own, a);
+        for (int64_t j = rank; j < R; j += world) {
+            const uint64_t id = ((uint64_t)a << 40) | (uint64_t)j;  // root index d = 0
+            const int out = rollout<P>(own, pool, board, first, h_card_value, seed, id);
+            stats[a * 3 + 0] += out; stats[a * 3 + 1] += (int64_t)out * out; stats[a * 3 + 2] += 1;
+        }
+    }
+    return 0;
+}
+
+extern "C" {
+int sim_mcs(int P_, const nimmt_root* root, int64_t R, uint64_t seed, int rank, int world, int64_t* stats) {
+    DISPATCH(P_, return mcs<P>(*root, R, seed, rank, world, stats));
+    return 0;
+}
+int sim_replay(int P_, int n, int turns, const int8_t* rows0, const int8_t* hands0, const int8_t* actions, int8_t* rewards,
+               uint8_t* done, uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores) {
+    DISPATCH(P_, replay<P>(n, turns, rows0, hands0, actions, rewards, done, illegal, hands, boards, scores));
+    return 0;
+}
+int sim_deal(int P_, int n, uint64_t seed, uint64_t game0, int8_t* hands, int8_t* boards) {
+    DISPATCH(P_, deal<P>(n, seed, game0, hands, boards));
+    return 0;
+}
+int sim_random_actions(int P_, int n, const int8_t* rows0, const int8_t* hands0, uint64_t seed, uint64_t game0, uint32_t turn,
+                       uint8_t* actions) {
+    DISPATCH(P_, rand_act<P>(n, rows0, hands0, seed, game0, turn, actions));
+    return 0;
+}
+int sim_check_sort_networks() {
+    int bad = 0;
+    bad |= check_network<2>(); bad |= check_network<3>(); bad |= check_network<4>(); bad |= check_network<5>();
+    bad |= check_network<6>(); bad |= check_network<7>(); bad |= check_network<8>(); bad |= check_network<9>();
+    bad |= check_network<10>();
+    return bad;
+}
+unsigned sim_select(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t k) { return mask_select(make_uint4(x, y, z, w), k); }
+}

@@ -1,0 +1,78 @@
+"""CPU differential test: the product's __host__ __device__ game logic (the exact code the CUDA
+kernels run per thread) against the oracle and the reference-generated goldens.  Catches logic
+bugs before GPU time is spent; the GPU parity tests (test_gpu_env.py) repeat this on the device."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN
+from host_sim import deal, lib, random_actions, replay
+
+
+def test_sorting_networks_zero_one_principle():
+    assert lib().sim_check_sort_networks() == 0
+
+
+def test_select_bit():
+    rng = np.random.RandomState(0)
+    for _ in range(2000):
+        cards = np.sort(rng.choice(104, rng.randint(1, 105), replace=False))
+        w = [0, 0, 0, 0]
+        for c in cards:
+            w[c >> 5] |= 1 << (c & 31)
+        k = rng.randint(len(cards))
+        assert lib().sim_select(w[0], w[1], w[2], w[3], k) == cards[k]
+
+
+@pytest.mark.parametrize("P", range(2, 11))
+def test_golden_traces(P):
+    z = np.load(os.path.join(GOLDEN, "env_traces.npz"))
+    g = lambda k: z[f"p{P}_{k}"]
+    out = replay(P, oracle.rows_from_singletons(g("deal_rows")), g("deal_hands"), g("actions"))
+    assert not out["illegal"].any()
+    for k in ("rewards", "done"):
+        assert (out[k] == g(k)).all(), k
+    for k in ("hands", "boards", "scores"):
+        assert (out[k] == g(k)[:, 1:]).all(), k
+
+
+@pytest.mark.parametrize("P", range(1, 11))
+def test_random_games_vs_oracle(P):
+    """Device-RNG deals + device-RNG actions, 10 turns, 3000 games: every byte equals the oracle's."""
+    n = 3000
+    hands, boards = deal(P, n, seed=77 + P)
+    # deals are valid: all cards distinct, hands ascending, one card per row
+    allc = np.concatenate([hands.reshape(n, -1), boards[:, :, 0]], axis=1)
+    assert (np.sort(allc, axis=1)[:, 1:] != np.sort(allc, axis=1)[:, :-1]).all()
+    assert (np.diff(hands.astype(int), axis=2) > 0).all() and (boards[:, :, 1:] == -1).all()
+    acts = np.zeros((n, 10, P), np.int8)
+    cur_h, cur_b = hands, boards
+    for t in range(10):
+        a = random_actions(P, cur_b, cur_h, seed=5, turn=t)
+        acts[:, t] = a.astype(np.int8)
+        step = oracle.replay(P, cur_b, cur_h, acts[:, t:t + 1], want_obs=False)
+        assert not step["illegal"].any()
+        cur_h, cur_b = step["hands"][:, 0], step["boards"][:, 0]
+    want = oracle.replay(P, boards, hands, acts, want_obs=False)
+    got = replay(P, boards, hands, acts)
+    for k in ("rewards", "done", "illegal", "hands", "boards", "scores"):
+        assert (got[k] == want[k]).all(), k
+    assert want["done"][:, -1].all() and not want["done"][:, :-1].any()
+
+
+def test_illegal_moves_untouched():
+    P, n = 4, 500
+    hands, boards = deal(P, n, seed=3)
+    acts = random_actions(P, boards, hands, seed=9, turn=0).astype(np.int8)[:, None, :]
+    bad = acts.copy()
+    # every 2nd game: player 2 plays a card that sits on the board
+    bad[::2, 0, 2] = boards[::2, 1, 0]
+    # every 5th game: out-of-range card id
+    bad[::5, 0, 0] = 120
+    want = oracle.replay(P, boards, hands, bad, want_obs=False)
+    got = replay(P, boards, hands, bad)
+    assert want["illegal"][::2].all() and want["illegal"].sum() < n
+    for k in ("rewards", "done", "illegal", "hands", "boards", "scores"):
+        assert (got[k] == want[k]).all(), k
