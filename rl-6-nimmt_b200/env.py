@@ -151,6 +151,19 @@ class BatchedSechsNimmtEnv:
             raise InvalidMoveException(f"game {bad}: a played card is not in its owner's hand")
         return self.rewards, self.done
 
+    def step_host(self, actions_host, rewards_host, done_host):
+        """step() for callers whose buffers live in (pinned) host memory — the end-to-end path.
+
+        Enqueues, on the current stream: H2D copy of ``actions_host`` (uint8 [B,P]), the step kernel,
+        D2H copies of rewards (int8 [B,P]) and done (uint8 [B]) into the given host tensors.  Nothing
+        synchronises; the caller syncs the stream (or an event) before reading the host buffers.
+        """
+        self._actions.copy_(actions_host, non_blocking=True)
+        self.step(self._actions)
+        rewards_host.copy_(self.rewards, non_blocking=True)
+        done_host.copy_(self.done, non_blocking=True)
+        return rewards_host, done_host
+
     def random_actions(self, out=None, turn=None):
         """DrunkHamster for every seat (agents/random.py:8-10): uint8 [B,P]."""
         out = self._actions if out is None else out
