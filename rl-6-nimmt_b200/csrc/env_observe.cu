@@ -38,16 +38,16 @@ k_observe(StateView s, T* __restrict__ obs, uint8_t* __restrict__ n_legal) {
         common[n++] = (int8_t)P;
         if constexpr (kSummaries) {
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) common[n + r] = (int8_t)(gm.board.meta[r] & 7u);
+            for (int r = 0; r < kRows; ++r) common[n + r] = (int8_t)gm.board.k.len(r);
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) common[n + 4 + r] = (int8_t)(gm.board.tk[r] >> 2);
+            for (int r = 0; r < kRows; ++r) common[n + 4 + r] = (int8_t)gm.board.k.top(r);
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) common[n + 8 + r] = (int8_t)(gm.board.meta[r] >> 3);
+            for (int r = 0; r < kRows; ++r) common[n + 8 + r] = (int8_t)gm.board.k.sum(r);
             n += 12;
         }
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
-            const int len = (int)(gm.board.meta[r] & 7u);
+            const int len = gm.board.k.len(r);
 #pragma unroll
             for (int i = 0; i < 6; ++i)
                 common[n + r * 6 + i] = i < len ? (int8_t)((gm.board.cards[r] >> (8 * i)) & 0xFF) : (int8_t)-1;

@@ -12,12 +12,13 @@ thread_local char g_last_error[256] = "";
 template <int P>
 __global__ void __launch_bounds__(kStepThreads) k_deal(StateView s, uint64_t seed, uint64_t game0) {
     __shared__ uint8_t values[128];
+    __shared__ __align__(4) uint8_t decks[kStepThreads * kDeckStride];
     stage_card_values(values);
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= s.B) return;
     Game<P> gm;
-    deal_game<P>(gm, seed, game0 + (uint64_t)g, values);
+    deal_game<P>(gm, seed, game0 + (uint64_t)g, values, decks + threadIdx.x * kDeckStride);
     store_game<P>(s, g, gm);
 }
 
@@ -41,9 +42,7 @@ __global__ void __launch_bounds__(kStepThreads) k_deal_from_perm(StateView s, co
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
         const uint32_t card = deck[kCards - 1 - r];
-        gm.board.tk[r] = (int)(card * 4u) + r;
-        gm.board.meta[r] = 1u | ((uint32_t)values[card & 127] << 3);
-        gm.board.cards[r] = card;
+        gm.board.set_row(r, card, card, 1u, values[card & 127]);
     }
     store_game<P>(s, g, gm);
 }
@@ -86,9 +85,7 @@ k_reset_to(StateView s, const int8_t* __restrict__ board, const int8_t* __restri
         }
         bad = bad || len == 0;
         if (len == 0) { len = 1; sum = values[0]; }  // keep the packed invariant 1 <= len <= 5
-        gm.board.cards[r] = cards;
-        gm.board.meta[r] = len | (sum << 3);
-        gm.board.tk[r] = (int)(top * 4u) + r;
+        gm.board.set_row(r, cards, top, len, sum);
     }
     const int8_t* hsrc = hands + g * (P * kHand);
 #pragma unroll

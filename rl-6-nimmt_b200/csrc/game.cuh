@@ -55,7 +55,7 @@ static const uint8_t h_card_value[128] = {NIMMT_CARD_VALUES};  // host copy (nim
 __device__ __forceinline__ void stage_card_values(uint8_t* smem) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(c_card_value);
     uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
-    for (int i = threadIdx.x; i < 32; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x < 32) dst[threadIdx.x] = src[threadIdx.x];
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -121,6 +121,17 @@ NIMMT_HD void mask_clear(uint4& m, uint32_t card) {
     m.w &= ~(word == 3 ? bit : 0u);
 }
 
+// Removes `card` from the set; returns whether it was there (false also for card ids >= 104).
+// One decode of the card into four word masks serves both the test and the removal.
+NIMMT_HD bool mask_take(uint4& m, uint32_t card, bool commit) {
+    const uint32_t word = card >> 5, bit = 1u << (card & 31);
+    const uint32_t b0 = word == 0 ? bit : 0u, b1 = word == 1 ? bit : 0u, b2 = word == 2 ? bit : 0u;
+    const uint32_t b3 = word == 3 ? (bit & kHighCardMask) : 0u;
+    const bool had = ((m.x & b0) | (m.y & b1) | (m.z & b2) | (m.w & b3)) != 0u;
+    if (commit) { m.x &= ~b0; m.y &= ~b1; m.z &= ~b2; m.w &= ~b3; }
+    return had;
+}
+
 NIMMT_HD void mask_set(uint4& m, uint32_t card) {
     const uint32_t word = card >> 5, bit = 1u << (card & 31);
     m.x |= (word == 0 ? bit : 0u);
@@ -161,18 +172,77 @@ NIMMT_HD uint32_t mask_select(const uint4& m, uint32_t k) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// Board: four rows in registers.
-//   tk[r]    = 4 * top card + r     (the +r makes "largest top below the card" one max and hands
-//                                    back the row index in the low two bits)
-//   meta[r]  = cards in row (bits 0..2) | bull-head sum of the row << 3   (the stored meta byte)
-//   cards[r] = byte i = i-th card of the row (oldest first); unused bytes are 0
+// Rows in registers.
+//
+// RowKeys is everything the dynamics depend on (env.py:138-172): per row the top card, the number
+// of cards and the bull-head sum, folded into two comparison keys so that a placement needs no
+// gather over rows:
+//   w[r] = top << 10 | sum << 5 | len << 2 | r     "largest top below the card" is max over the
+//                                                   rows with w < card << 10, and the winner's
+//                                                   sum, len and index come along in its low bits
+//   u[r] = sum << 2 | r                             the undercut rule (lowest sum, lowest index on
+//                                                   ties) is min over u
+// Board adds the card lists (needed for observations / bit-exact state, not for the dynamics):
+//   cards[r] = byte i = i-th card of the row, oldest first; unused bytes are 0.
 // ----------------------------------------------------------------------------------------------
+struct RowKeys {
+    int w[kRows];
+    int u[kRows];
+
+    NIMMT_HD void set_row(int r, uint32_t top, uint32_t len, uint32_t sum) {
+        w[r] = (int)((top << 10) | (sum << 5) | (len << 2) | (uint32_t)r);
+        u[r] = (int)((sum << 2) | (uint32_t)r);
+    }
+    NIMMT_HD int top(int r) const { return w[r] >> 10; }
+    NIMMT_HD int len(int r) const { return (w[r] >> 2) & 7; }
+    NIMMT_HD int sum(int r) const { return (w[r] >> 5) & 31; }
+
+    // One placement (env.py:126-134 + _find_row :138-152 + _pick_row_to_replace :154-159 +
+    // _score_row :161-172).  Returns the bull heads taken (0 if none); `row` and `keep_len` tell the
+    // caller where the card went (keep_len = cards of the row that stay under it: 0 after a take).
+    //   undercut (card below every top) -> row with the smallest bull-head sum, lowest index on
+    //                                      ties; the player takes the whole old row
+    //   otherwise                       -> row with the largest top below the card; if it already
+    //                                      holds five cards the player takes those five
+    // In both take cases the penalty is the row's sum BEFORE the append and the row restarts with
+    // the played card alone.
+    NIMMT_HD int place(int card, int value, int& row, uint32_t& keep_len) {
+        const int ck = card << 10;
+        const int n0 = w[0] < ck ? w[0] : -1, n1 = w[1] < ck ? w[1] : -1;
+        const int n2 = w[2] < ck ? w[2] : -1, n3 = w[3] < ck ? w[3] : -1;
+        const int best = imax(imax(n0, n1), imax(n2, n3));
+        const int cheapest = imin(imin(u[0], u[1]), imin(u[2], u[3]));
+        const bool under = best < 0;
+        const int r = (under ? cheapest : best) & 3;
+        const uint32_t len = ((uint32_t)best >> 2) & 7u;  // garbage when under; take is true then
+        const uint32_t sum = under ? (uint32_t)cheapest >> 2 : ((uint32_t)best >> 5) & 31u;
+        const bool take = under || len == 5u;
+        keep_len = take ? 0u : len;
+        const uint32_t new_sum = (take ? 0u : sum) + (uint32_t)value;
+        const int new_w = ck | (int)((new_sum << 5) | ((keep_len + 1u) << 2)) | r;
+        const int new_u = (int)(new_sum << 2) | r;
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {  // selects, not branches: a warp's 32 games pick different rows
+            const bool hit = r == i;
+            w[i] = hit ? new_w : w[i];
+            u[i] = hit ? new_u : u[i];
+        }
+        row = r;
+        return take ? (int)sum : 0;
+    }
+};
+
 struct Board {
-    int tk[kRows];
-    uint32_t meta[kRows];
+    RowKeys k;
     uint64_t cards[kRows];
 
-    // Unpacks the 24-byte row block (three little-endian 64-bit words).
+    NIMMT_HD void set_row(int r, uint64_t row_cards, uint32_t top, uint32_t len, uint32_t sum) {
+        k.set_row(r, top, len, sum);
+        cards[r] = row_cards;
+    }
+
+    // Unpacks the 24-byte row block (three little-endian 64-bit words): 4 x (5 card bytes + meta
+    // byte = len | sum << 3).
     NIMMT_HD void unpack(uint64_t q0, uint64_t q1, uint64_t q2) {
         uint64_t rb[kRows];
         rb[0] = q0;
@@ -182,56 +252,35 @@ struct Board {
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
             cards[r] = rb[r] & 0xFFFFFFFFFFull;
-            meta[r] = (uint32_t)(rb[r] >> 40) & 0xFFu;
-            const uint32_t len = meta[r] & 7u;
+            const uint32_t meta = (uint32_t)(rb[r] >> 40) & 0xFFu;
+            const uint32_t len = meta & 7u;
             const uint32_t top = (uint32_t)(cards[r] >> (8u * (len - 1u))) & 0xFFu;
-            tk[r] = (int)(top * 4u) + r;
+            k.set_row(r, top, len, meta >> 3);
         }
     }
 
     NIMMT_HD void pack(uint64_t& q0, uint64_t& q1, uint64_t& q2) const {
         uint64_t rb[kRows];
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) rb[r] = cards[r] | ((uint64_t)meta[r] << 40);
+        for (int r = 0; r < kRows; ++r) {
+            const uint32_t meta = (uint32_t)k.len(r) | ((uint32_t)k.sum(r) << 3);
+            rb[r] = cards[r] | ((uint64_t)meta << 40);
+        }
         q0 = rb[0] | (rb[1] << 48);
         q1 = (rb[1] >> 16) | (rb[2] << 32);
         q2 = (rb[2] >> 32) | (rb[3] << 16);
     }
 
-    // One placement (env.py:126-134 + _find_row :138-152 + _pick_row_to_replace :154-159 +
-    // _score_row :161-172).  Returns the bull heads taken (0 if none).
-    //   undercut (card below every top)   -> row with the smallest bull-head sum, lowest index on
-    //                                        ties; the player takes the whole old row
-    //   otherwise                         -> row with the largest top below the card; if it
-    //                                        already holds five cards the player takes those five
-    // In both take cases the penalty is the row's sum BEFORE the append and the row restarts with
-    // the played card alone.
     NIMMT_HD int place(int card, int value) {
-        const int c4 = card * 4;
-        const int n0 = tk[0] < c4 ? tk[0] : -1, n1 = tk[1] < c4 ? tk[1] : -1;
-        const int n2 = tk[2] < c4 ? tk[2] : -1, n3 = tk[3] < c4 ? tk[3] : -1;
-        const int best = imax(imax(n0, n1), imax(n2, n3));
-        const bool under = best < 0;
-        // argmin over (sum, row): meta >> 3 is the sum; low bits carry the row index
-        const int u0 = (int)((meta[0] >> 3) << 2), u1 = (int)((meta[1] >> 3) << 2) | 1;
-        const int u2 = (int)((meta[2] >> 3) << 2) | 2, u3 = (int)((meta[3] >> 3) << 2) | 3;
-        const int cheapest = imin(imin(u0, u1), imin(u2, u3));
-        const int r = (under ? cheapest : best) & 3;
-        const bool is0 = r == 0, is1 = r == 1, is2 = r == 2;
-        const uint32_t m = is0 ? meta[0] : is1 ? meta[1] : is2 ? meta[2] : meta[3];
-        const uint64_t cr = is0 ? cards[0] : is1 ? cards[1] : is2 ? cards[2] : cards[3];
-        const uint32_t len = m & 7u, sum = m >> 3;
-        const bool take = under || len == 5u;
-        const int penalty = take ? (int)sum : 0;
-        const uint32_t keep_len = take ? 0u : len;
-        const uint32_t new_meta = (keep_len + 1u) | (((take ? 0u : sum) + (uint32_t)value) << 3);
-        const uint64_t new_cards = (take ? 0ull : cr) | ((uint64_t)(uint32_t)card << (8u * keep_len));
+        int r;
+        uint32_t keep_len;
+        const int penalty = k.place(card, value, r, keep_len);
+        const uint64_t keep = keep_len ? ~0ull : 0ull;   // keep_len == 0 <=> the row restarts
+        const uint64_t shifted = (uint64_t)(uint32_t)card << (8u * keep_len);
 #pragma unroll
         for (int i = 0; i < kRows; ++i) {
-            const bool hit = r == i;
-            tk[i] = hit ? c4 + i : tk[i];
-            meta[i] = hit ? new_meta : meta[i];
-            cards[i] = hit ? new_cards : cards[i];
+            const uint64_t appended = (cards[i] & keep) | shifted;
+            cards[i] = r == i ? appended : cards[i];
         }
         return penalty;
     }

@@ -20,35 +20,8 @@
 
 namespace nimmt {
 
-// Rows without their card lists: enough for playouts.
-struct BoardLite {
-    int tk[kRows];          // 4 * top + row
-    uint32_t meta[kRows];   // len | sum << 3
-
-    // Same rule as Board::place (game.cuh), minus the card bookkeeping.
-    NIMMT_HD int place(int card, int value) {
-        const int c4 = card * 4;
-        const int n0 = tk[0] < c4 ? tk[0] : -1, n1 = tk[1] < c4 ? tk[1] : -1;
-        const int n2 = tk[2] < c4 ? tk[2] : -1, n3 = tk[3] < c4 ? tk[3] : -1;
-        const int best = imax(imax(n0, n1), imax(n2, n3));
-        const bool under = best < 0;
-        const int u0 = (int)((meta[0] >> 3) << 2), u1 = (int)((meta[1] >> 3) << 2) | 1;
-        const int u2 = (int)((meta[2] >> 3) << 2) | 2, u3 = (int)((meta[3] >> 3) << 2) | 3;
-        const int cheapest = imin(imin(u0, u1), imin(u2, u3));
-        const int r = (under ? cheapest : best) & 3;
-        const uint32_t m = r == 0 ? meta[0] : r == 1 ? meta[1] : r == 2 ? meta[2] : meta[3];
-        const uint32_t len = m & 7u, sum = m >> 3;
-        const bool take = under || len == 5u;
-        const uint32_t new_meta = ((take ? 0u : len) + 1u) | (((take ? 0u : sum) + (uint32_t)value) << 3);
-#pragma unroll
-        for (int i = 0; i < kRows; ++i) {
-            const bool hit = r == i;
-            tk[i] = hit ? c4 + i : tk[i];
-            meta[i] = hit ? new_meta : meta[i];
-        }
-        return take ? (int)sum : 0;
-    }
-};
+// Rows without their card lists (RowKeys, game.cuh) are enough for playouts.
+using BoardLite = RowKeys;
 
 // Decodes a root position (BaseMCAgent's view of the game, agents/mcts.py:62-89) into rollout
 // state.  Cards in the own hand or lying on the board are never "unseen" (mcts.py:66-73), whatever
@@ -71,8 +44,7 @@ NIMMT_HD bool decode_root(const nimmt_root& root, const uint8_t* values, uint4& 
             }
         }
         if (len == 0) return false;
-        board.tk[r] = (int)(top * 4u) + r;
-        board.meta[r] = len | (sum << 3);
+        board.set_row(r, top, len, sum);
     }
     return root.num_players == P && mask_count(pool) >= (P - 1) * mask_count(own);
 }
@@ -117,7 +89,9 @@ NIMMT_HD int rollout(uint4 own, uint4 pool, BoardLite board, int first, const ui
 #pragma unroll
         for (int i = 0; i < P; ++i) {
             const int card = keys[i] >> 4;
-            const int pen = board.place(card, values[card]);
+            int row;
+            uint32_t keep_len;
+            const int pen = board.place(card, values[card], row, keep_len);
             outcome -= (keys[i] & 15) == 0 ? pen : 0;   // mcts.py:150: player 0's rewards only
         }
         first_turn = false;

@@ -34,11 +34,15 @@ template <> struct PenaltyPack<5> { using type = uint32_t; };
 // (env.py:68-69: every move is checked before anything is mutated).
 template <int P>
 NIMMT_HD bool step_game(Game<P>& g, const int (&act)[P], const uint8_t* values, int (&penalty)[P]) {
+    // env.py:68-69 + :131 — every card is checked (and tentatively removed) before anything is committed
+    uint4 hand[P];
     bool legal = true;
 #pragma unroll
-    for (int p = 0; p < P; ++p) legal = legal && mask_has(g.hand[p], (uint32_t)act[p]);
-#pragma unroll
-    for (int p = 0; p < P; ++p) penalty[p] = 0;
+    for (int p = 0; p < P; ++p) {
+        hand[p] = g.hand[p];
+        legal = mask_take(hand[p], (uint32_t)act[p], true) && legal;
+        penalty[p] = 0;
+    }
     if (!legal) return false;
 
     // sorted((card, player)) ascending by card (env.py:124-125)
@@ -57,8 +61,8 @@ NIMMT_HD bool step_game(Game<P>& g, const int (&act)[P], const uint8_t* values, 
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         penalty[p] = (int)((packed >> (6 * p)) & 63u);
-        mask_clear(g.hand[p], (uint32_t)act[p]);              // env.py:131
-        g.hand[p].w += (uint32_t)penalty[p] << kScoreShift;   // env.py:167
+        hand[p].w += (uint32_t)penalty[p] << kScoreShift;     // env.py:167
+        g.hand[p] = hand[p];
     }
     return true;
 }
@@ -69,22 +73,26 @@ NIMMT_HD bool game_done(const Game<P>& g) {
     return (g.hand[0].x | g.hand[0].y | g.hand[0].z | (g.hand[0].w & kHighCardMask)) == 0u;
 }
 
-// SechsNimmtEnv._deal (env.py:99-112) with a counter RNG: 10 P + 4 draws without replacement
-// from the 104-card deck.  Draw i < 10 P goes to hand i / 10 (the reference's perm[10p .. 10p+9]),
-// draw 10 P + r opens row r (the reference's perm[103 - r]): a prefix plus four more entries of a
-// uniform permutation, which is all the reference's shuffle provides.
+// SechsNimmtEnv._deal (env.py:99-112) with a counter RNG: a partial Fisher-Yates shuffle of the
+// 104-card deck, 10 P + 4 draws.  Draw i < 10 P goes to hand i / 10 (the reference's
+// perm[10p .. 10p+9]), draw 10 P + r opens row r (the reference's perm[103 - r]): a prefix plus
+// four more entries of a uniform permutation, which is all the reference's shuffle provides.
+// `deck` is 104 bytes of scratch private to this game (a slice of shared memory on the device,
+// kDeckStride bytes apart so that equal indices of different threads fall in different banks).
+constexpr int kDeckStride = 116;  // 29 words: odd word stride
+
 template <int P>
-NIMMT_HD void deal_game(Game<P>& g, uint64_t seed, uint64_t game_id, const uint8_t* values) {
+NIMMT_HD void deal_game(Game<P>& g, uint64_t seed, uint64_t game_id, const uint8_t* values, uint8_t* deck) {
     Philox rng(seed, game_id, /*stream=*/0x6e696d74u, 0);
-    uint4 deck = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, kHighCardMask);
-    uint32_t left = kCards;
+#pragma unroll
+    for (int i = 0; i < kCards / 4; ++i) reinterpret_cast<uint32_t*>(deck)[i] = 0x03020100u + 0x04040404u * (uint32_t)i;
     uint4 r = make_uint4(0, 0, 0, 0);
     auto draw = [&](int i) -> uint32_t {
         if ((i & 3) == 0) r = rng.next();
         const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-        const uint32_t card = mask_select(deck, below(word, left));
-        mask_clear(deck, card);
-        --left;
+        const uint32_t j = (uint32_t)i + below(word, (uint32_t)(kCards - i));
+        const uint32_t card = deck[j];
+        deck[j] = deck[i];   // position i is never read again, so only half of the swap is needed
         return card;
     };
 #pragma unroll
@@ -97,9 +105,7 @@ NIMMT_HD void deal_game(Game<P>& g, uint64_t seed, uint64_t game_id, const uint8
 #pragma unroll
     for (int row = 0; row < kRows; ++row) {
         const uint32_t card = draw(P * kHand + row);
-        g.board.tk[row] = (int)(card * 4u) + row;
-        g.board.meta[row] = 1u | ((uint32_t)values[card] << 3);
-        g.board.cards[row] = card;
+        g.board.set_row(row, card, card, 1u, values[card]);
     }
 }
 

@@ -24,7 +24,7 @@ static void unpack_to_arrays(const Game<P>& g, int8_t* hands /*[P][10]*/, int8_t
     Board b;
     b.unpack(q0, q1, q2);
     for (int r = 0; r < kRows; ++r) {
-        const int len = b.meta[r] & 7;
+        const int len = b.k.len(r);
         for (int i = 0; i < 6; ++i) board[r * 6 + i] = i < len ? (int8_t)((b.cards[r] >> (8 * i)) & 0xFF) : -1;
     }
 }
@@ -39,9 +39,7 @@ static void init_game(Game<P>& g, const int8_t* rows0 /*[4][6]*/, const int8_t* 
             cards |= (uint64_t)c << (8 * len);
             ++len; sum += h_card_value[c]; top = c;
         }
-        g.board.cards[r] = cards;
-        g.board.meta[r] = len | (sum << 3);
-        g.board.tk[r] = top * 4 + r;
+        g.board.set_row(r, cards, top, len, sum);
     }
     for (int p = 0; p < P; ++p) {
         g.hand[p] = make_uint4(0, 0, 0, 0);
@@ -74,7 +72,8 @@ static void deal(int n, uint64_t seed, uint64_t game0, int8_t* hands, int8_t* bo
     int16_t sc[P];
     for (int gi = 0; gi < n; ++gi) {
         Game<P> g;
-        deal_game<P>(g, seed, game0 + gi, h_card_value);
+        alignas(4) uint8_t deck[kDeckStride];
+        deal_game<P>(g, seed, game0 + gi, h_card_value, deck);
         unpack_to_arrays<P>(g, hands + (size_t)gi * P * 10, boards + (size_t)gi * 24, sc);
     }
 }
