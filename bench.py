@@ -209,26 +209,45 @@ def run_ours(args):
             ev[1].record()
         launches += 1
 
+    CYCLE = NSETS * 10   # steps after which every batch has played one full game and sits at turn 10 again
+
     for i in range(max(W, 3)):
         one_step(i)
+    for i in range((-max(W, 3)) % CYCLE):   # untimed: bring every batch back to a game boundary
+        one_step(max(W, 3) + i)
+    barrier()
+    # The inner loop is launch-bound from Python (a k_step launch is ~35 us of GPU time), so one
+    # cycle of 40 steps + 4 re-deals is captured once into a CUDA graph and replayed.
+    graph = torch.cuda.CUDAGraph()
+    launches = 0
+    with torch.cuda.graph(graph):
+        for i in range(CYCLE):
+            one_step(i)
+    launches_per_cycle = launches
+    for env in envs:
+        env.turn = 10
+    graph.replay()   # warm the instantiated graph
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    step_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches = 0
     barrier()
     t_begin = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(K):
-        one_step(W + i, step_events[i])
+    for _ in range(K // CYCLE):
+        graph.replay()
+    for env in envs:
+        env.turn = 10
+    for i in range(K % CYCLE):   # the remainder, eagerly: exactly K steps are timed
+        one_step(i)
     e1.record()
     barrier()
     t_end = time.perf_counter()
     elapsed_ms = e0.elapsed_time(e1)
-    timed_launches = launches
+    timed_launches = launches + (K // CYCLE) * launches_per_cycle
     illegal = sum(int(e.illegal.any()) for e in envs)
     assert illegal == 0, "random legal actions were rejected"
     if world > 1:
@@ -237,7 +256,35 @@ def run_ours(args):
         elapsed_ms = float(t.item())
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     value = world * B * K / (elapsed_ms * 1e-3)
-    kstep_ms = statistics.mean(a.elapsed_time(b) for a, b in step_events)
+
+    # ---- the dominant kernel on its own: the same cycle split into two graphs, the 4 re-deals and the
+    # 40 k_step launches, with CUDA events around the latter.  (Events around every single launch add
+    # ~5 us each to a ~34 us kernel, and eager launches from Python cannot keep the queue full.) ----
+    for i in range((-(K % CYCLE)) % CYCLE):
+        one_step((K % CYCLE) + i)
+    barrier()
+    g_deal, g_steps = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_deal):
+        for env in envs:
+            env.reset(seed=env.seed)
+    with torch.cuda.graph(g_steps):
+        for i in range(CYCLE):
+            env = envs[i % NSETS]
+            env.step(tapes[i % NSETS][i // NSETS])
+    reps = 5
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    g_deal.replay(); g_steps.replay()
+    barrier()
+    for a, b_ in pairs:
+        g_deal.replay()
+        a.record()
+        g_steps.replay()
+        b_.record()
+    barrier()
+    assert sum(int(e.illegal.any()) for e in envs) == 0
+    for env in envs:
+        env.turn = 10
+    kstep_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in pairs) / CYCLE
 
     # ---- end to end: host buffers in, host buffers out, every step ---------------------------------
     # Legal action sequences are recorded once (untimed) into pinned host memory by playing each
@@ -256,26 +303,32 @@ def run_ours(args):
     K2 = max(NSETS * 10, min(K, 2000))
     K2 -= K2 % (NSETS * 10)
 
-    def e2e_pass(n_steps):
-        for i in range(n_steps):
-            s = i % NSETS
-            env = envs[s]
+    def e2e_cycle():
+        """One full game of every batch through the host-buffer API, each batch on its own stream:
+        deal, then ten times (actions H2D -> k_step -> rewards + done D2H)."""
+        for s, env in enumerate(envs):
             with torch.cuda.stream(streams[s]):
-                if env.turn == 10 or i < NSETS:
-                    env.reset(seed=99 + s)
-                env.step_host(h_actions[s][env.turn], h_rewards[s], h_done[s])
+                env.reset(seed=99 + s)
+                for t in range(10):
+                    env.step_host(h_actions[s][t], h_rewards[s], h_done[s])
 
-    e2e_pass(NSETS * 10)  # warm-up: one full game per batch
+    e2e_cycle()  # warm-up, eager
     barrier()
-    main = torch.cuda.current_stream(dev)
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):   # fork the four chains off the capture stream, join them back
+        cap = torch.cuda.current_stream(dev)
+        for st in streams:
+            st.wait_stream(cap)
+        e2e_cycle()
+        for st in streams:
+            cap.wait_stream(st)
+    g2.replay()
+    barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(main)
-    for st in streams:
-        st.wait_event(f0)
-    e2e_pass(K2)
-    for st in streams:
-        main.wait_stream(st)
-    f1.record(main)
+    f0.record()
+    for _ in range(K2 // CYCLE):
+        g2.replay()
+    f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1)
     assert all(int(e.illegal.any()) == 0 for e in envs) and all(bool(d.all()) for d in h_done), "e2e replay diverged"
@@ -291,6 +344,7 @@ def run_ours(args):
             fn(i)
         barrier()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(int(4e7))   # hold the GPU while the host enqueues: measures kernels, not launch latency
         a.record()
         for i in range(n):
             fn(i)
@@ -351,12 +405,13 @@ def run_ours(args):
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "players": P, "games_per_gpu_per_step": B,
                    "l2": f"{NSETS} independent batches visited round-robin ({NSETS} x {(16 * P + 24 + 2 * P + 2) * B / 1e6:.0f} MB > 126 MB L2), no explicit flush",
-                   "step": "k_step over recorded uniformly random legal actions resident in HBM, + k_deal every 10th visit of a batch", "seed": 1234},
+                   "step": "k_step over recorded uniformly random legal actions resident in HBM, + k_deal every 10th visit of a batch; 40-step cycles replayed as a CUDA graph", "seed": 1234},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": traffic, "kernel": "k_step<4,false>", "kernel_ms": kstep_ms,
+                     "traffic": traffic, "kernel": "k_step_smem<4>", "kernel_ms": kstep_ms,
+                     "how": "CUDA events around a graph of 40 back-to-back k_step launches (4 batches x 10 turns), mean of 5",
                      "algorithmic_bytes_per_launch": bytes_per_step(P) * B, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * P, "d2h_bytes_per_step": B * P + B, "steps": K2,
-                "api": "BatchedSechsNimmtEnv.step_host (pinned host actions in, rewards+done out), 4 batches on 4 streams"},
+                "api": "BatchedSechsNimmtEnv.step_host (pinned host actions in, rewards+done out), 4 batches on 4 streams, 40-step cycles replayed as a CUDA graph"},
         "gpu_launches": timed_launches,
         "clocks": clocks,
         "also": {"k_random_actions_ms": ra_ms, "k_deal_ms": deal_ms,

@@ -21,24 +21,23 @@ __device__ __forceinline__ void load_game(const StateView& s, int64_t g, Game<P>
 template <int P>
 struct RawGame {
     uint4 hand[P];
-    uint4 rows_a;
-    uint2 rows_b;
+    uint2 rows[3];
 };
 
 template <int P>
 __device__ __forceinline__ void load_raw(const StateView& s, int64_t g, RawGame<P>& raw) {
 #pragma unroll
     for (int p = 0; p < P; ++p) raw.hand[p] = s.hand[(int64_t)p * s.B + g];
-    raw.rows_a = s.rows_a[g];
-    raw.rows_b = s.rows_b[g];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) raw.rows[k] = s.rows[3 * g + k];
 }
 
 template <int P>
 __device__ __forceinline__ void unpack_raw(const RawGame<P>& raw, Game<P>& gm) {
 #pragma unroll
     for (int p = 0; p < P; ++p) gm.hand[p] = raw.hand[p];
-    gm.board.unpack((uint64_t)raw.rows_a.x | ((uint64_t)raw.rows_a.y << 32), (uint64_t)raw.rows_a.z | ((uint64_t)raw.rows_a.w << 32),
-                    (uint64_t)raw.rows_b.x | ((uint64_t)raw.rows_b.y << 32));
+    gm.board.unpack((uint64_t)raw.rows[0].x | ((uint64_t)raw.rows[0].y << 32), (uint64_t)raw.rows[1].x | ((uint64_t)raw.rows[1].y << 32),
+                    (uint64_t)raw.rows[2].x | ((uint64_t)raw.rows[2].y << 32));
 }
 
 template <int P>

@@ -50,108 +50,224 @@ k_step(StateView s, const uint8_t* __restrict__ actions_in, uint8_t* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// k_step_tiles — the same step, for whole tiles of 128 games, with the loads taken off the
-// threads: one elected thread asks the TMA engine (cp.async.bulk, 1-D) to stream the next tile's
-// planes — P hand planes of 2 KB, the 2 KB + 1 KB row planes, 128 P action bytes, each one
-// contiguous in HBM — into the other half of a double buffer while the block steps the current
-// tile out of shared memory.  A thread therefore never sits on outstanding loads with its 70
-// registers pinned, and every block keeps one to two tiles (12-24 KB for P = 4) in flight the
-// whole time, which is what it takes to cover HBM latency at ~40 % occupancy.
-// Stores go straight from registers (16-byte, warp-contiguous).  Each block owns kTilesPerBlock
-// consecutive tiles; the ragged tail of the batch is left to k_step.
+// k_step_smem — the throughput path of env.step.  HBM <-> shared memory is done entirely by the TMA
+// engine (1-D cp.async.bulk, both directions); the threads never issue a global load or store.
+//
+// Each WARP runs its own double-buffered pipeline over tiles of 32 games, with no block-level
+// synchronisation at all:
+//     lane 0:  bulk-load tile i+1's planes (P hand planes of 512 B, 768 B of row records, 32 P
+//              action bytes — each contiguous in HBM) into the other buffer        [mbarrier]
+//     lanes:   step tile i IN PLACE in shared memory — clear one bit of each hand word, write one
+//              card byte of the row record, bump a score byte; the only per-row state kept in
+//              registers is the two comparison keys of game.cuh::RowKeys
+//     lane 0:  bulk-store the tile's planes plus rewards / done / illegal          [bulk group]
+// Working in place is what makes the kernel cheap: the plain k_step spends most of its ALU-pipe
+// slots selecting among register-resident rows and packing / unpacking them; here a placement is
+// one byte store at a computed shared-memory address.
 // ------------------------------------------------------------------------------------------
-constexpr int kTileGames = 128;
-constexpr int kTilesPerBlock = 4;
+constexpr int kTileGames = 32;
+constexpr int kSmemWarps = 4;   // warps per block; each is independent
 
 template <int P>
 struct TileLayout {
     static constexpr int kHandPlane = kTileGames * 16;
-    static constexpr int kRowsA = P * kHandPlane;
-    static constexpr int kRowsB = kRowsA + kTileGames * 16;
-    static constexpr int kActions = kRowsB + kTileGames * 8;
-    static constexpr int kBytes = kActions + kTileGames * P;   // multiple of 16 for every P
+    static constexpr int kRows = P * kHandPlane;                 // 24-byte records
+    static constexpr int kActions = kRows + kTileGames * 24;
+    static constexpr int kLoadBytes = kActions + kTileGames * P; // everything above is loaded
+    static constexpr int kRewards = kLoadBytes;
+    static constexpr int kDone = kRewards + kTileGames * P;
+    static constexpr int kIllegal = kDone + kTileGames;
+    static constexpr int kBytes = kIllegal + kTileGames;
     static constexpr int kStride = (kBytes + 127) / 128 * 128;
+    static_assert(kActions % 16 == 0 && kRewards % 16 == 0 && kDone % 16 == 0 && kIllegal % 16 == 0, "bulk copies need 16-byte alignment");
 };
 
 template <int P>
-__device__ __forceinline__ void issue_tile(const StateView& s, const uint8_t* actions, int64_t tile, uint8_t* dst, uint64_t* bar) {
+__device__ __forceinline__ void issue_tile_loads(const StateView& s, const uint8_t* actions, int64_t tile, uint8_t* buf, uint64_t* bar) {
     using L = TileLayout<P>;
     const int64_t g0 = tile * kTileGames;
-    mbar_arrive_expect_tx(bar, L::kBytes);
+    mbar_arrive_expect_tx(bar, L::kLoadBytes);
 #pragma unroll
-    for (int p = 0; p < P; ++p) bulk_load(dst + p * L::kHandPlane, s.hand + (int64_t)p * s.B + g0, L::kHandPlane, bar);
-    bulk_load(dst + L::kRowsA, s.rows_a + g0, kTileGames * 16, bar);
-    bulk_load(dst + L::kRowsB, s.rows_b + g0, kTileGames * 8, bar);
-    bulk_load(dst + L::kActions, actions + g0 * P, kTileGames * P, bar);
+    for (int p = 0; p < P; ++p) bulk_load(buf + p * L::kHandPlane, s.hand + (int64_t)p * s.B + g0, L::kHandPlane, bar);
+    bulk_load(buf + L::kRows, s.rows + 3 * g0, kTileGames * 24, bar);
+    bulk_load(buf + L::kActions, actions + g0 * P, kTileGames * P, bar);
 }
 
 template <int P>
-__global__ void __launch_bounds__(kTileGames)
-k_step_tiles(StateView s, const uint8_t* __restrict__ actions, int8_t* __restrict__ rewards, uint8_t* __restrict__ done,
-             uint8_t* __restrict__ illegal, int64_t num_tiles) {
+__device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* rewards, uint8_t* done, uint8_t* illegal, int64_t tile,
+                                                  const uint8_t* buf) {
     using L = TileLayout<P>;
-    extern __shared__ __align__(128) uint8_t tile_smem[];   // 2 x L::kStride
-    __shared__ uint64_t full[2];
+    const int64_t g0 = tile * kTileGames;
+#pragma unroll
+    for (int p = 0; p < P; ++p) bulk_store(s.hand + (int64_t)p * s.B + g0, buf + p * L::kHandPlane, L::kHandPlane);
+    bulk_store(s.rows + 3 * g0, buf + L::kRows, kTileGames * 24);
+    bulk_store(rewards + g0 * P, buf + L::kRewards, kTileGames * P);
+    bulk_store(done + g0, buf + L::kDone, kTileGames);
+    if (illegal) bulk_store(illegal + g0, buf + L::kIllegal, kTileGames);
+    bulk_commit();
+}
+
+// One game, in place in the tile buffer.  `lane` selects the game.
+template <int P>
+__device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8_t* values) {
+    using L = TileLayout<P>;
+    uint8_t* hand0 = buf + lane * 16;          // + p * kHandPlane
+    uint8_t* rec = buf + L::kRows + lane * 24;
+
+    int act[P];
+    load_bytes<P>(buf + L::kActions, lane, act);
+
+    // env.py:68-69 — check every card before touching anything
+    uint32_t word[P], bit[P];
+    int amax = 0;
+    bool legal = true;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        word[p] = *reinterpret_cast<const uint32_t*>(hand0 + p * L::kHandPlane + ((act[p] >> 3) & 12));
+        bit[p] = 1u << (act[p] & 31);
+        legal = legal && (word[p] & bit[p]) != 0u;
+        amax = imax(amax, act[p]);
+    }
+    legal = legal && amax < kCards;
+
+    uint32_t rew_words[(P + 3) / 4];
+#pragma unroll
+    for (int i = 0; i < (P + 3) / 4; ++i) rew_words[i] = 0;
+
+    if (legal) {
+#pragma unroll
+        for (int p = 0; p < P; ++p)   // env.py:131
+            *reinterpret_cast<uint32_t*>(hand0 + p * L::kHandPlane + ((act[p] >> 3) & 12)) = word[p] & ~bit[p];
+
+        // comparison keys of the four rows (game.cuh::RowKeys) from the record
+        RowKeys rk;
+        const uint32_t metas = *reinterpret_cast<const uint32_t*>(rec + 20);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const uint32_t meta = (metas >> (8 * r)) & 0xFFu;
+            const uint32_t top = rec[4 * ((meta & 7u) - 1u) + r];
+            rk.w[r] = (int)((top << 10) | (meta << 2) | (uint32_t)r);
+            rk.u[r] = (int)(((meta >> 3) << 2) | (uint32_t)r);
+        }
+
+        int keys[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) keys[p] = (act[p] << 4) | p;
+        sort_keys<P>(keys);   // env.py:124-125
+
+        typename PenaltyPack<P>::type packed = 0;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const int card = keys[i] >> 4, player = keys[i] & 15;
+            int row;
+            uint32_t keep_len;
+            const int pen = rk.place(card, values[card], row, keep_len);   // env.py:126-134
+            uint8_t* col = rec + row;
+            col[4 * keep_len] = (uint8_t)card;
+            if (keep_len == 0) {   // the row restarts: clear its other four slots (canonical record)
+                col[4] = 0; col[8] = 0; col[12] = 0; col[16] = 0;
+            }
+            packed += (typename PenaltyPack<P>::type)pen << (6 * player);
+        }
+
+        uint32_t new_metas = 0;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) new_metas |= (((uint32_t)rk.w[r] >> 2) & 0xFFu) << (8 * r);
+        *reinterpret_cast<uint32_t*>(rec + 20) = new_metas;
+
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const uint32_t pen = (uint32_t)((packed >> (6 * p)) & 63u);
+            uint8_t* score = hand0 + p * L::kHandPlane + 15;
+            *score = (uint8_t)(*score + pen);                                   // env.py:167
+            rew_words[p / 4] |= ((0u - pen) & 0xFFu) << (8 * (p & 3));          // env.py:169
+        }
+    }
+    // outputs
+    {
+        uint8_t* rw = buf + L::kRewards + lane * P;
+        if constexpr (P % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < P / 4; ++i) reinterpret_cast<uint32_t*>(rw)[i] = rew_words[i];
+        } else if constexpr (P % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < P / 2; ++i) reinterpret_cast<uint16_t*>(rw)[i] = (uint16_t)(rew_words[i / 2] >> (16 * (i & 1)));
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) rw[p] = (uint8_t)(rew_words[p / 4] >> (8 * (p & 3)));
+        }
+        const uint4 h0 = *reinterpret_cast<const uint4*>(hand0);
+        buf[L::kDone + lane] = (h0.x | h0.y | h0.z | (h0.w & kHighCardMask)) == 0u;   // env.py:246-249
+        buf[L::kIllegal + lane] = !legal;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(kSmemWarps * 32)
+k_step_smem(StateView s, const uint8_t* __restrict__ actions, int8_t* __restrict__ rewards, uint8_t* __restrict__ done,
+            uint8_t* __restrict__ illegal, int64_t num_tiles) {
+    using L = TileLayout<P>;
+    extern __shared__ __align__(128) uint8_t tile_smem[];   // kSmemWarps x 2 x L::kStride
+    __shared__ uint64_t full[kSmemWarps][2];
     __shared__ uint8_t values[128];
 
-    const int64_t first = (int64_t)blockIdx.x * kTilesPerBlock;
-    const int n_tiles = (int)min((int64_t)kTilesPerBlock, num_tiles - first);
-    if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* bufs = tile_smem + warp * 2 * L::kStride;
+    const int64_t stride = (int64_t)gridDim.x * kSmemWarps;
+    int64_t tile = (int64_t)blockIdx.x * kSmemWarps + warp;
+
+    if (lane == 0) {
+        mbar_init(&full[warp][0], 1);
+        mbar_init(&full[warp][1], 1);
         fence_barrier_init();
-        issue_tile<P>(s, actions, first, tile_smem, &full[0]);
-        if (n_tiles > 1) issue_tile<P>(s, actions, first + 1, tile_smem + L::kStride, &full[1]);
+        if (tile < num_tiles) issue_tile_loads<P>(s, actions, tile, bufs, &full[warp][0]);
+        if (tile + stride < num_tiles) issue_tile_loads<P>(s, actions, tile + stride, bufs + L::kStride, &full[warp][1]);
     }
     stage_card_values(values);
-    __syncthreads();
+    __syncthreads();   // the only block-wide barrier: value table + barrier init
 
-    for (int it = 0; it < n_tiles; ++it) {
-        const int stage = it & 1;
-        const uint8_t* buf = tile_smem + stage * L::kStride;
-        mbar_wait(&full[stage], (uint32_t)(it >> 1) & 1u);
-
-        RawGame<P> raw;
-#pragma unroll
-        for (int p = 0; p < P; ++p) raw.hand[p] = reinterpret_cast<const uint4*>(buf + p * L::kHandPlane)[threadIdx.x];
-        raw.rows_a = reinterpret_cast<const uint4*>(buf + L::kRowsA)[threadIdx.x];
-        raw.rows_b = reinterpret_cast<const uint2*>(buf + L::kRowsB)[threadIdx.x];
-        int act[P];
-        load_bytes<P>(buf + L::kActions, threadIdx.x, act);
-        __syncthreads();   // every thread holds its game: this half of the buffer is free again
-        if (threadIdx.x == 0 && it + 2 < n_tiles) issue_tile<P>(s, actions, first + it + 2, tile_smem + stage * L::kStride, &full[stage]);
-
-        const int64_t g = (first + it) * kTileGames + threadIdx.x;
-        Game<P> gm;
-        unpack_raw<P>(raw, gm);
-        int penalty[P];
-        const bool legal = step_game<P>(gm, act, values, penalty);
-        if (legal) store_game<P>(s, g, gm);
-        int rew[P];
-#pragma unroll
-        for (int p = 0; p < P; ++p) rew[p] = -penalty[p];
-        store_bytes<P>(reinterpret_cast<uint8_t*>(rewards), g, rew);
-        done[g] = game_done<P>(gm);
-        if (illegal) illegal[g] = !legal;
+    for (int it = 0; tile < num_tiles; tile += stride, ++it) {
+        const int b = it & 1;
+        uint8_t* buf = bufs + b * L::kStride;
+        mbar_wait(&full[warp][b], (uint32_t)(it >> 1) & 1u);
+        step_in_smem<P>(buf, lane, values);
+        fence_async_smem();   // make this lane's shared-memory writes visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+            issue_tile_stores<P>(s, rewards, done, illegal, tile, buf);
+            if (tile + 2 * stride < num_tiles) {
+                bulk_wait_read0();   // the engine has read the buffer: it may be refilled
+                issue_tile_loads<P>(s, actions, tile + 2 * stride, buf, &full[warp][b]);
+            }
+        }
+        __syncwarp();
     }
+    if (lane == 0) bulk_wait_all();   // stores must land before the block's shared memory is released
 }
 
 template <int P>
 static int launch_step(const StateView& s, const uint8_t* actions, int8_t* rewards, uint8_t* done, uint8_t* illegal, cudaStream_t st) {
     using L = TileLayout<P>;
-    constexpr int kSmem = 2 * L::kStride;
+    constexpr int kSmem = kSmemWarps * 2 * L::kStride;
     const int64_t num_tiles = s.B / kTileGames;
     if (num_tiles > 0) {
-        static bool configured = false;   // benign race: the attribute is idempotent
-        if (!configured) {
-            cudaFuncSetAttribute(k_step_tiles<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-            configured = true;
+        static int blocks_per_sm = 0, num_sms = 0;   // benign race: both queries are idempotent
+        if (blocks_per_sm == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(k_step_smem<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_smem<P>, kSmemWarps * 32, kSmem);
+            blocks_per_sm = occ > 0 ? occ : 1;
         }
-        const unsigned blocks = (unsigned)((num_tiles + kTilesPerBlock - 1) / kTilesPerBlock);
-        k_step_tiles<P><<<blocks, kTileGames, kSmem, st>>>(s, actions, rewards, done, illegal, num_tiles);
+        // persistent grid: one resident wave; every warp walks tiles warp_id, warp_id + #warps, ...
+        const int64_t want = (num_tiles + kSmemWarps - 1) / kSmemWarps;
+        const unsigned blocks = (unsigned)min(want, (int64_t)num_sms * blocks_per_sm);
+        k_step_smem<P><<<blocks, kSmemWarps * 32, kSmem, st>>>(s, actions, rewards, done, illegal, num_tiles);
     }
     const int64_t tail0 = num_tiles * kTileGames;
-    if (tail0 < s.B)   // ragged tail (< 128 games): plain loads
+    if (tail0 < s.B)   // ragged tail (< 32 games): plain loads
         k_step<P, false><<<1, kStepThreads, 0, st>>>(s, actions, nullptr, rewards, done, illegal, 0, 0, 0, tail0);
     return 0;
 }
@@ -182,7 +298,7 @@ int nimmt_step(void* state, const uint8_t* actions, int8_t* rewards, uint8_t* do
                int num_players, void* stream) {
     if (int rc = check_common(state, B, num_players)) return rc;
     if (!actions || !rewards || !done) return NIMMT_E_BADARG;
-    if (!aligned16(actions) || !aligned16(rewards)) return NIMMT_E_ALIGN;
+    if (!aligned16(actions) || !aligned16(rewards) || !aligned16(done) || (illegal && !aligned16(illegal))) return NIMMT_E_ALIGN;
     if (B == 0) return NIMMT_OK;
     StateView s(state, B, num_players);
     NIMMT_DISPATCH_P(num_players, launch_step<P>(s, actions, rewards, done, illegal, (cudaStream_t)stream));

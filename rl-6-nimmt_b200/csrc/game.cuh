@@ -241,34 +241,37 @@ struct Board {
         cards[r] = row_cards;
     }
 
-    // Unpacks the 24-byte row block (three little-endian 64-bit words): 4 x (5 card bytes + meta
-    // byte = len | sum << 3).
+    // The stored 24-byte row record is slot-major: byte 4 j + r = j-th card (oldest first) of row r
+    // for j = 0..4, byte 20 + r = meta of row r (len | sum << 3).  A placement touches exactly one
+    // byte of it (plus the meta bytes), which is what lets k_step_smem update it in place.
+    // q0 / q1 / q2 are its three little-endian 64-bit words.
     NIMMT_HD void unpack(uint64_t q0, uint64_t q1, uint64_t q2) {
-        uint64_t rb[kRows];
-        rb[0] = q0;
-        rb[1] = (q0 >> 48) | (q1 << 16);
-        rb[2] = (q1 >> 32) | (q2 << 32);
-        rb[3] = q2 >> 16;
+        const uint32_t slot[5] = {(uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32), (uint32_t)q2};
+        const uint32_t metas = (uint32_t)(q2 >> 32);
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
-            cards[r] = rb[r] & 0xFFFFFFFFFFull;
-            const uint32_t meta = (uint32_t)(rb[r] >> 40) & 0xFFu;
+            uint64_t c = 0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) c |= (uint64_t)((slot[j] >> (8 * r)) & 0xFFu) << (8 * j);
+            cards[r] = c;
+            const uint32_t meta = (metas >> (8 * r)) & 0xFFu;
             const uint32_t len = meta & 7u;
-            const uint32_t top = (uint32_t)(cards[r] >> (8u * (len - 1u))) & 0xFFu;
+            const uint32_t top = (uint32_t)(c >> (8u * (len - 1u))) & 0xFFu;
             k.set_row(r, top, len, meta >> 3);
         }
     }
 
     NIMMT_HD void pack(uint64_t& q0, uint64_t& q1, uint64_t& q2) const {
-        uint64_t rb[kRows];
+        uint32_t slot[5] = {0, 0, 0, 0, 0}, metas = 0;
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
-            const uint32_t meta = (uint32_t)k.len(r) | ((uint32_t)k.sum(r) << 3);
-            rb[r] = cards[r] | ((uint64_t)meta << 40);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) slot[j] |= (uint32_t)((cards[r] >> (8 * j)) & 0xFFu) << (8 * r);
+            metas |= ((uint32_t)k.len(r) | ((uint32_t)k.sum(r) << 3)) << (8 * r);
         }
-        q0 = rb[0] | (rb[1] << 48);
-        q1 = (rb[1] >> 16) | (rb[2] << 32);
-        q2 = (rb[2] >> 32) | (rb[3] << 16);
+        q0 = (uint64_t)slot[0] | ((uint64_t)slot[1] << 32);
+        q1 = (uint64_t)slot[2] | ((uint64_t)slot[3] << 32);
+        q2 = (uint64_t)slot[4] | ((uint64_t)metas << 32);
     }
 
     NIMMT_HD int place(int card, int value) {
@@ -334,29 +337,26 @@ NIMMT_HD void sort_keys(int (&k)[N]) {
 // Packed-state addressing (SoA planes, include/nimmt_b200.h).
 // ----------------------------------------------------------------------------------------------
 struct StateView {
-    uint4* hand;    // [P][B]
-    uint4* rows_a;  // [B]
-    uint2* rows_b;  // [B]
+    uint4* hand;   // [P][B]  128-bit hand words, one plane per player
+    uint2* rows;   // [B][3]  24-byte row records
     int64_t B;
     __host__ __device__ StateView(void* base, int64_t num_games, int num_players) : B(num_games) {
         hand = reinterpret_cast<uint4*>(base);
-        rows_a = hand + (int64_t)num_players * num_games;
-        rows_b = reinterpret_cast<uint2*>(rows_a + num_games);
+        rows = reinterpret_cast<uint2*>(hand + (int64_t)num_players * num_games);
     }
 };
 
 NIMMT_HD void load_rows(const StateView& s, int64_t g, Board& b) {
-    const uint4 a = s.rows_a[g];
-    const uint2 c = s.rows_b[g];
-    b.unpack((uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)a.z | ((uint64_t)a.w << 32),
-             (uint64_t)c.x | ((uint64_t)c.y << 32));
+    const uint2 a = s.rows[3 * g], c = s.rows[3 * g + 1], d = s.rows[3 * g + 2];
+    b.unpack((uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)c.x | ((uint64_t)c.y << 32), (uint64_t)d.x | ((uint64_t)d.y << 32));
 }
 
 NIMMT_HD void store_rows(const StateView& s, int64_t g, const Board& b) {
     uint64_t q0, q1, q2;
     b.pack(q0, q1, q2);
-    s.rows_a[g] = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32));
-    s.rows_b[g] = make_uint2((uint32_t)q2, (uint32_t)(q2 >> 32));
+    s.rows[3 * g] = make_uint2((uint32_t)q0, (uint32_t)(q0 >> 32));
+    s.rows[3 * g + 1] = make_uint2((uint32_t)q1, (uint32_t)(q1 >> 32));
+    s.rows[3 * g + 2] = make_uint2((uint32_t)q2, (uint32_t)(q2 >> 32));
 }
 
 }  // namespace nimmt

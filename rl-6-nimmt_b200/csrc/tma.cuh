@@ -43,4 +43,17 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                  : "memory");
 }
 
+// 1-D bulk copy shared -> global (bulk-group completion).  Shared-memory writes made by ordinary
+// stores must be fenced into the async proxy (fence_async_smem) before this is issued.
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Waits until the engine has finished READING the shared-memory sources of all committed groups
+// (the buffers may be overwritten; the global writes may still be in flight).
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 }  // namespace nimmt
