@@ -130,9 +130,18 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
     }
     legal = legal && amax < kCards;
 
-    uint32_t rew_words[(P + 3) / 4];
+    // rewards default to 0 (env.py:122); a take overwrites its player's byte below
+    uint8_t* rw = buf + L::kRewards + lane * P;
+    if constexpr (P % 4 == 0) {
 #pragma unroll
-    for (int i = 0; i < (P + 3) / 4; ++i) rew_words[i] = 0;
+        for (int i = 0; i < P / 4; ++i) reinterpret_cast<uint32_t*>(rw)[i] = 0u;
+    } else if constexpr (P % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < P / 2; ++i) reinterpret_cast<uint16_t*>(rw)[i] = 0;
+    } else {
+#pragma unroll
+        for (int p = 0; p < P; ++p) rw[p] = 0;
+    }
 
     if (legal) {
 #pragma unroll
@@ -155,47 +164,27 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
         for (int p = 0; p < P; ++p) keys[p] = (act[p] << 4) | p;
         sort_keys<P>(keys);   // env.py:124-125
 
-        typename PenaltyPack<P>::type packed = 0;
 #pragma unroll
         for (int i = 0; i < P; ++i) {
             const int card = keys[i] >> 4, player = keys[i] & 15;
             int row;
             uint32_t keep_len;
             const int pen = rk.place(card, values[card], row, keep_len);   // env.py:126-134
-            uint8_t* col = rec + row;
-            col[4 * keep_len] = (uint8_t)card;
-            if (keep_len == 0) {   // the row restarts: clear its other four slots (canonical record)
-                col[4] = 0; col[8] = 0; col[12] = 0; col[16] = 0;
+            rec[4 * keep_len + row] = (uint8_t)card;   // the one byte of the record a placement changes
+            if (pen != 0) {                            // a take (rare): env.py:167-169
+                uint8_t* score = hand0 + player * L::kHandPlane + 15;
+                *score = (uint8_t)(*score + pen);
+                rw[player] = (uint8_t)(0 - pen);
             }
-            packed += (typename PenaltyPack<P>::type)pen << (6 * player);
         }
 
         uint32_t new_metas = 0;
 #pragma unroll
         for (int r = 0; r < kRows; ++r) new_metas |= (((uint32_t)rk.w[r] >> 2) & 0xFFu) << (8 * r);
         *reinterpret_cast<uint32_t*>(rec + 20) = new_metas;
-
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const uint32_t pen = (uint32_t)((packed >> (6 * p)) & 63u);
-            uint8_t* score = hand0 + p * L::kHandPlane + 15;
-            *score = (uint8_t)(*score + pen);                                   // env.py:167
-            rew_words[p / 4] |= ((0u - pen) & 0xFFu) << (8 * (p & 3));          // env.py:169
-        }
     }
     // outputs
     {
-        uint8_t* rw = buf + L::kRewards + lane * P;
-        if constexpr (P % 4 == 0) {
-#pragma unroll
-            for (int i = 0; i < P / 4; ++i) reinterpret_cast<uint32_t*>(rw)[i] = rew_words[i];
-        } else if constexpr (P % 2 == 0) {
-#pragma unroll
-            for (int i = 0; i < P / 2; ++i) reinterpret_cast<uint16_t*>(rw)[i] = (uint16_t)(rew_words[i / 2] >> (16 * (i & 1)));
-        } else {
-#pragma unroll
-            for (int p = 0; p < P; ++p) rw[p] = (uint8_t)(rew_words[p / 4] >> (8 * (p & 3)));
-        }
         const uint4 h0 = *reinterpret_cast<const uint4*>(hand0);
         buf[L::kDone + lane] = (h0.x | h0.y | h0.z | (h0.w & kHighCardMask)) == 0u;   // env.py:246-249
         buf[L::kIllegal + lane] = !legal;
@@ -203,7 +192,7 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
 }
 
 template <int P>
-__global__ void __launch_bounds__(kSmemWarps * 32)
+__global__ void __launch_bounds__(kSmemWarps * 32, 8)
 k_step_smem(StateView s, const uint8_t* __restrict__ actions, int8_t* __restrict__ rewards, uint8_t* __restrict__ done,
             uint8_t* __restrict__ illegal, int64_t num_tiles) {
     using L = TileLayout<P>;

@@ -33,6 +33,7 @@ NIMMT_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
 }
 NIMMT_HD int imin(int a, int b) { return a < b ? a : b; }
 NIMMT_HD int imax(int a, int b) { return a > b ? a : b; }
+NIMMT_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 constexpr int kRows = 4;
 constexpr int kCards = 104;
@@ -183,7 +184,8 @@ NIMMT_HD uint32_t mask_select(const uint4& m, uint32_t k) {
 //   u[r] = sum << 2 | r                             the undercut rule (lowest sum, lowest index on
 //                                                   ties) is min over u
 // Board adds the card lists (needed for observations / bit-exact state, not for the dynamics):
-//   cards[r] = byte i = i-th card of the row, oldest first; unused bytes are 0.
+//   cards[r] = byte i = i-th card of the row, oldest first; bytes at index >= len are unspecified
+//              (zero after a deal / reset_to, stale cards after a take).
 // ----------------------------------------------------------------------------------------------
 struct RowKeys {
     int w[kRows];
@@ -208,11 +210,13 @@ struct RowKeys {
     // the played card alone.
     NIMMT_HD int place(int card, int value, int& row, uint32_t& keep_len) {
         const int ck = card << 10;
-        const int n0 = w[0] < ck ? w[0] : -1, n1 = w[1] < ck ? w[1] : -1;
-        const int n2 = w[2] < ck ? w[2] : -1, n3 = w[3] < ck ? w[3] : -1;
-        const int best = imax(imax(n0, n1), imax(n2, n3));
+        // largest w below ck == smallest positive ck - w; rows above the card wrap to huge unsigned values
+        const uint32_t d0 = (uint32_t)(ck - w[0]), d1 = (uint32_t)(ck - w[1]);
+        const uint32_t d2 = (uint32_t)(ck - w[2]), d3 = (uint32_t)(ck - w[3]);
+        const uint32_t dmin = umin32(umin32(d0, d1), umin32(d2, d3));
+        const int best = ck - (int)dmin;
         const int cheapest = imin(imin(u[0], u[1]), imin(u[2], u[3]));
-        const bool under = best < 0;
+        const bool under = dmin > (uint32_t)ck;   // card below every top
         const int r = (under ? cheapest : best) & 3;
         const uint32_t len = ((uint32_t)best >> 2) & 7u;  // garbage when under; take is true then
         const uint32_t sum = under ? (uint32_t)cheapest >> 2 : ((uint32_t)best >> 5) & 31u;
@@ -278,12 +282,14 @@ struct Board {
         int r;
         uint32_t keep_len;
         const int penalty = k.place(card, value, r, keep_len);
-        const uint64_t keep = keep_len ? ~0ull : 0ull;   // keep_len == 0 <=> the row restarts
-        const uint64_t shifted = (uint64_t)(uint32_t)card << (8u * keep_len);
+        // write the one slot the card lands in; slots at index >= len keep whatever they held
+        // (they are unspecified in the stored record: k_step_smem writes a single byte too)
+        const uint32_t shift = 8u * keep_len;
+        const uint64_t clear = ~(0xFFull << shift), put = (uint64_t)(uint32_t)card << shift;
 #pragma unroll
         for (int i = 0; i < kRows; ++i) {
-            const uint64_t appended = (cards[i] & keep) | shifted;
-            cards[i] = r == i ? appended : cards[i];
+            const uint64_t written = (cards[i] & clear) | put;
+            cards[i] = r == i ? written : cards[i];
         }
         return penalty;
     }
