@@ -150,6 +150,30 @@ typedef struct nimmt_root {
 NIMMT_API int nimmt_mcs_rollouts(const nimmt_root *roots, int num_roots, int num_players, int64_t rollouts_per_action,
                                  uint64_t seed, int rank, int world, int64_t *stats, void *stream);
 
+/* ---- Alpha0.5 leaf evaluation (the only dense GEMM on the path; tcgen05 tensor cores) ---- */
+
+/* Bytes of the packed policy-weight blob consumed by the kernels below. */
+NIMMT_API size_t nimmt_policy_weights_bytes(void);
+
+/* HOST function.  Packs the fp32 parameters of PolicyMCSAgent.actor = MultiHeadedMLP(48, (100, 100), (1,))
+ * (utils/nets.py:100-132; torch Linear layout: w1 [100][48], w2 [100][100], w3 [100]) into `blob_host`
+ * (nimmt_policy_weights_bytes() bytes of host memory): SechsNimmtStateNormalization(action=True)
+ * (utils/preprocessing.py:12-57) is folded into layer 1, matrices are rounded to bf16 and laid out as
+ * tcgen05 K-major shared-memory operands, hidden width padded 100 -> 112 with zeros.  Copy the blob to
+ * the device once per weight update. */
+NIMMT_API int nimmt_policy_pack_weights(const float *w1, const float *b1, const float *w2, const float *b2,
+                                        const float *w3, float b3, void *blob_host);
+
+/* PolicyMCSAgent._compute_policy (agents/mcts.py:219-228) for D decisions at once.
+ *   obs     int8  [D][47]  observation of the deciding player (nimmt_observe layout, NIMMT_DT_I8);
+ *                          its legal cards are the non-negative entries of obs[d][0..9]
+ *   weights device copy of the packed blob
+ *   probs   float [D][10]  softmax over the legal cards, by hand slot; 0 for empty slots
+ *   logits  float [D][10]  may be NULL; the pre-softmax head outputs
+ * bf16 operands, fp32 accumulation: probabilities agree with the fp32 reference to ~2e-4. */
+NIMMT_API int nimmt_policy_probs(const int8_t *obs, int64_t num_decisions, const void *weights, float *probs,
+                                 float *logits, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

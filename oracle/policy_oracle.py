@@ -91,3 +91,33 @@ def puct_choice(p):
         if v > best:
             best, choice = v, i
     return choice
+
+
+# ----------------------------------------------------------------------------------------------
+# Emulation of what the tcgen05 kernel computes, for sharp kernel tests: normalisation folded
+# into layer 1, bf16 operands, fp32 accumulation, hidden layer 1 rounded to bf16, layer 3 in fp32.
+# The fp32 functions above remain the reference semantics; this one only explains the rounding.
+# ----------------------------------------------------------------------------------------------
+def _bf16(x):
+    """Round-to-nearest-even to bfloat16, returned as float32."""
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+def fold_normalization(w):
+    """(W1', b1') with W1' x_raw + b1' == W1 normalize(x_raw) + b1 (preprocessing.py:56-57 is affine)."""
+    scale, shift = normalization_affine()
+    w1 = w["w1"].astype(np.float64)
+    return (w1 * scale[None, :]).astype(np.float32), (w["b1"].astype(np.float64) + w1 @ shift).astype(np.float32)
+
+
+def policy_logits_bf16(rows, w):
+    w1f, b1f = fold_normalization(w)
+    x = _bf16(rows)                      # raw features are small integers: exact
+    h1 = np.maximum(x @ _bf16(w1f).T + b1f, 0.0).astype(np.float32)
+    h2 = np.maximum(_bf16(h1) @ _bf16(w["w2"]).T + w["b2"], 0.0).astype(np.float32)
+    return (h2 @ w["w3"].reshape(-1).astype(np.float32) + np.float32(w["b3"].reshape(-1)[0])).astype(np.float32)
+
+
+def policy_probs_bf16(rows, w):
+    return softmax(policy_logits_bf16(rows, w))

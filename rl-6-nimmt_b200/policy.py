@@ -1,0 +1,62 @@
+"""Host side of the Alpha0.5 policy net (PolicyMCSAgent.actor, agents/mcts.py:194-228).
+
+The network is the reference's: ``MultiHeadedMLP(48, (100, 100), (1,))`` with ReLU
+(utils/nets.py:100-132) behind ``SechsNimmtStateNormalization(action=True)``
+(utils/preprocessing.py:12-57).  It lives in PyTorch as an ``nn.Module`` with the reference's
+parameter names (so its state_dict is interchangeable and autograd trains it); for inference the
+parameters are packed once into a device blob and evaluated by the tcgen05 kernel.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import _native as N
+
+
+class PolicyNet(nn.Module):
+    """Same parameter tree as the reference's ``actor`` (``latent_net.{0,2}``, ``head_nets.0.0``)."""
+
+    def __init__(self, input_size=48, hidden_sizes=(100, 100)):
+        super().__init__()
+        if (input_size, tuple(hidden_sizes)) != (48, (100, 100)):
+            raise NotImplementedError("the tcgen05 kernel is built for the reference's 48-100-100-1 policy net")
+        self.latent_net = nn.Sequential(nn.Linear(48, 100), nn.ReLU(), nn.Linear(100, 100), nn.ReLU())
+        self.head_nets = nn.ModuleList([nn.Sequential(nn.Linear(100, 1))])
+
+    def forward(self, inputs):          # fp32 torch path: training only (agents/mcts.py:230-261)
+        latent = self.latent_net(inputs)
+        return [head(latent) for head in self.head_nets]
+
+
+def pack_weights(net, device=None):
+    """Packs a PolicyNet (or anything with the same state_dict keys) into the device blob."""
+    lib = N.lib()
+    sd = {k: v.detach().to("cpu", torch.float32).contiguous().numpy() for k, v in net.state_dict().items()}
+    w1, b1 = sd["latent_net.0.weight"], sd["latent_net.0.bias"]
+    w2, b2 = sd["latent_net.2.weight"], sd["latent_net.2.bias"]
+    w3, b3 = sd["head_nets.0.0.weight"].reshape(-1), float(sd["head_nets.0.0.bias"].reshape(-1)[0])
+    assert w1.shape == (100, 48) and w2.shape == (100, 100) and w3.shape == (100,)
+    blob = np.zeros(lib.nimmt_policy_weights_bytes(), np.uint8)
+    ptr = lambda a: np.ascontiguousarray(a).ctypes.data
+    N.check(lib.nimmt_policy_pack_weights(ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), b3, blob.ctypes.data), "nimmt_policy_pack_weights")
+    t = torch.from_numpy(blob)
+    if device is not None or torch.cuda.is_available():
+        t = t.to(device if device is not None else "cuda")
+    return t
+
+
+def policy_probs(obs, weights, want_logits=False):
+    """PolicyMCSAgent._compute_policy for a batch: obs int8 [D,47] (device) -> probs float32 [D,10]
+    by hand slot (0 for empty slots)."""
+    if not torch.cuda.is_available():
+        raise N.NimmtNativeError("policy_probs needs a CUDA device; there is no CPU fallback")
+    lib = N.lib()
+    assert obs.dtype == torch.int8 and obs.is_cuda and obs.dim() == 2 and obs.shape[1] == 47
+    obs = obs.contiguous()
+    D = obs.shape[0]
+    probs = torch.empty((D, 10), dtype=torch.float32, device=obs.device)
+    logits = torch.empty((D, 10), dtype=torch.float32, device=obs.device) if want_logits else None
+    with torch.cuda.device(obs.device):
+        N.check(lib.nimmt_policy_probs(N.ptr(obs), D, N.ptr(weights), N.ptr(probs), N.ptr(logits),
+                                       torch.cuda.current_stream(obs.device).cuda_stream), "nimmt_policy_probs")
+    return (probs, logits) if want_logits else probs
