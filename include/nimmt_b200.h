@@ -174,6 +174,26 @@ NIMMT_API int nimmt_policy_pack_weights(const float *w1, const float *b1, const 
 NIMMT_API int nimmt_policy_probs(const int8_t *obs, int64_t num_decisions, const void *weights, float *probs,
                                  float *logits, void *stream);
 
+/* root-move rules of nimmt_policy_rollouts */
+#define NIMMT_ROOT_PUCT 0        /* PUCTAgent._choose_action_mc (agents/mcts.py:276-293) */
+#define NIMMT_ROOT_POLICY 1      /* PolicyMCSAgent._choose_action_mc (agents/mcts.py:209-217): sampled from the policy */
+#define NIMMT_ROOT_STRATIFIED 2  /* rollout j starts with legal card j mod n (equal budgets; for evaluation and tests) */
+
+/* BaseMCAgent._mcts (agents/mcts.py:91-103) for PolicyMCSAgent / PUCTAgent ("Alpha0.5"), D decisions at once:
+ * n_mc sequential rollouts per root; in each, the opponents are dealt from the root's available cards
+ * (agents/mcts.py:116-127), every move of every player is sampled from softmax(policy net) over that
+ * player's legal cards (agents/mcts.py:139-147, 209-228) except player 0's first move, which follows
+ * `root_rule`; the outcome (sum of player 0's rewards, agents/mcts.py:150) is filed under the first card.
+ *   stats      int64 [D][10][3]  = (sum outcome, sum outcome^2, visits) per legal card (by rank in the own hand);
+ *                                  OVERWRITTEN for playable roots, untouched for skipped ones (see nimmt_mcs_rollouts)
+ *   root_probs float [D][10]      policy at the root (what PUCT uses as prior; log of it is the agent's log_prob)
+ * The caller applies the final rule (_choose_action_from_outcomes, agents/mcts.py:156-165) to `stats`.
+ * A search is inherently sequential (PUCT reads all earlier outcomes), so one decision is never split over
+ * GPUs; shard the D roots instead. */
+NIMMT_API int nimmt_policy_rollouts(const nimmt_root *roots, int num_roots, int num_players, const void *weights, int n_mc,
+                                    float c_puct, int root_rule, uint64_t seed, int64_t *stats, float *root_probs,
+                                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

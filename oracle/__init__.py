@@ -50,6 +50,10 @@ def lib():
         L.oracle_bench_env.restype = ctypes.c_int64
         L.oracle_bench_mcs.argtypes = [ctypes.c_int, i32p, i32p, ctypes.c_int, i32p, ctypes.c_int,
                                        ctypes.c_int64, ctypes.c_int, ctypes.c_uint64, i64p]
+        f32p = ctypes.POINTER(ctypes.c_float)
+        L.oracle_policy_rollouts.argtypes = [ctypes.c_int, i32p, i32p, ctypes.c_int, i32p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64,
+                                             ctypes.c_int, f32p, f32p, f32p, f32p, f32p, ctypes.c_float, i64p]
+        L.oracle_policy_probs.argtypes = [ctypes.c_void_p, i32p, i32p, ctypes.c_int, f32p]
         L.oracle_deal_from_perm.argtypes = [ctypes.c_void_p, ctypes.c_int, i32p]
         _lib = L
     return _lib
@@ -144,4 +148,24 @@ def bench_mcs(num_players, board, own, available, rollouts_per_thread, n_threads
                                 int(seed), _p(stats, ctypes.c_int64))
     if rc:
         raise ValueError(f"oracle_bench_mcs failed ({rc})")
+    return stats
+
+
+def policy_rollouts(num_players, board, own, available, n_rollouts, weights, seed=0, first_action=-1):
+    """Reference-style PolicyMCSAgent rollouts in fp32 (agents/mcts.py:91-154, 209-228).
+    weights: dict w1 [100,48], b1, w2 [100,100], b2, w3 [1,100] or [100], b3.  Returns int64 [len(own),3]."""
+    rows = -np.ones((4, 6), np.int32)
+    for r, cards in enumerate(board):
+        rows[r, : len(cards)] = cards
+    own = np.ascontiguousarray(own, dtype=np.int32)
+    available = np.ascontiguousarray(available, dtype=np.int32)
+    w = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()}
+    stats = np.zeros((len(own), 3), np.int64)
+    rc = lib().oracle_policy_rollouts(num_players, _p(rows, ctypes.c_int), _p(own, ctypes.c_int), len(own), _p(available, ctypes.c_int),
+                                      len(available), int(n_rollouts), int(seed), int(first_action),
+                                      _p(w["w1"], ctypes.c_float), _p(w["b1"], ctypes.c_float), _p(w["w2"], ctypes.c_float),
+                                      _p(w["b2"], ctypes.c_float), _p(w["w3"].reshape(-1), ctypes.c_float), float(w["b3"].reshape(-1)[0]),
+                                      _p(stats, ctypes.c_int64))
+    if rc:
+        raise ValueError(f"oracle_policy_rollouts failed ({rc})")
     return stats

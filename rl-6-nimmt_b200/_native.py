@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libnimmt_b200.so")
 ABI_VERSION = 1
 OK, E_BADARG, E_ALIGN, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -3, -4
 DT_I8, DT_I16, DT_F32, DT_I64 = 0, 1, 2, 3
+ROOT_PUCT, ROOT_POLICY, ROOT_STRATIFIED = 0, 1, 2
 
 _ERRORS = {E_BADARG: "bad argument", E_ALIGN: "misaligned pointer", E_CUDA: "CUDA error", E_UNSUPPORTED: "unsupported"}
 
@@ -48,6 +49,7 @@ SIGNATURES = {
     "nimmt_policy_weights_bytes": (ctypes.c_size_t, []),
     "nimmt_policy_pack_weights": (_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_float, _vp]),
     "nimmt_policy_probs": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "nimmt_policy_rollouts": (_int, [_vp, _int, _int, _vp, _int, ctypes.c_float, _int, _u64, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -11,6 +11,8 @@ import math
 import numpy as np
 import torch
 
+from .. import _native as N
+from .. import policy as PL
 from .. import rollouts as R
 from .base import Agent
 
@@ -109,3 +111,87 @@ class MCSAgent(BaseMCAgent):
 
     def learn(self, *args, **kwargs):
         pass
+
+
+class PolicyMCSAgent(BaseMCAgent):
+    """Monte-Carlo search whose playouts follow a learnable policy (agents/mcts.py:191-261).
+
+    The policy net keeps the reference's parameter names (``actor.latent_net.0.weight`` ...), so state
+    dicts are interchangeable.  Searches run in k_policy_rollouts (tcgen05 policy net + env dynamics on
+    chip); the imitation update of ``learn`` stays in PyTorch autograd, as in the reference.
+    """
+
+    root_rule = N.ROOT_POLICY
+
+    def __init__(self, hidden_sizes=(100, 100), activation=None, r_factor=0.1, **kwargs):
+        super().__init__(**kwargs)
+        self.r_factor = r_factor
+        self.actor = PL.PolicyNet(self.state_length + 1, hidden_sizes)
+        self._packed, self._packed_key = None, None
+        self.last_root_probs = None
+
+    def _weights(self):
+        key = tuple(int(p._version) for p in self.actor.parameters())   # bumped by every optimizer step / load
+        if self._packed is None or key != self._packed_key:
+            self._packed, self._packed_key = PL.pack_weights(self.actor), key
+        return self._packed
+
+    def _compute_policy(self, legal_actions, state):
+        return PL.torch_policy(self.actor, state, legal_actions)
+
+    def _search_kwargs(self):
+        return {}
+
+    def _mcts(self, legal_actions, state):
+        legal_actions = [int(a) for a in legal_actions]
+        root = R.pack_root_from_state(state, legal_actions, self.available_cards)
+        n_mc = self._compute_n_mc(len(legal_actions)) if self.rollouts_per_card is None else self.rollouts_per_card * len(legal_actions)
+        seed = (self._seed * 0x9E3779B1 + self._decisions) & (2**64 - 1)
+        self._decisions += 1
+        stats, probs = R.policy_rollouts(root[None], self.num_players, self._weights(), n_mc, root_rule=self.root_rule, seed=seed,
+                                         **self._search_kwargs())
+        self.last_stats = stats[0].cpu().numpy()[: len(legal_actions)]
+        self.last_root_probs = probs[0].cpu().numpy()[: len(legal_actions)]
+        action, means = R.choose_from_stats(legal_actions, self.last_stats)          # mcts.py:156-165
+        # info["log_prob"] = log pi(chosen card | root) (mcts.py:165, 215, 293), with autograd for learn()
+        log_prob = torch.log(self._compute_policy(legal_actions, state)[legal_actions.index(action)])
+        if logger.isEnabledFor(logging.DEBUG):
+            logger.debug("AlphaAlmostZero thoughts:")
+            for a, m, row, p in zip(legal_actions, means, self.last_stats, self.last_root_probs):
+                logger.debug(f"  {'x' if a == action else ' '} {a + 1:>3d}: p = {p:.2f}, n = {int(row[2]):>3d}, E[r] = {m:>5.1f}")
+        return action, {"log_prob": log_prob}
+
+    def learn(self, state, reward, action, done, next_state, next_reward, episode_end, num_episode, legal_actions, *args, **kwargs):
+        self.history.store(log_prob=kwargs["log_prob"], reward=reward * self.r_factor)      # mcts.py:232
+        if not episode_end or not self.training:
+            return 0.0
+        loss = self._train()
+        self.history.clear()
+        return loss
+
+    def _train(self):
+        log_probs = torch.stack([lp for lp in self.history.rollout()["log_prob"] if lp.requires_grad] or [torch.zeros((), requires_grad=True)], dim=0)
+        loss = -torch.sum(log_probs)           # imitate the (deterministic) search choice, mcts.py:246-249
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+        return loss.item()
+
+
+class PUCTAgent(PolicyMCSAgent):
+    """"Alpha0.5" (agents/mcts.py:264-323): PUCT over the root statistics, policy playouts below."""
+
+    root_rule = N.ROOT_PUCT
+
+    def __init__(self, c_puct=2.0, temperature=None, **kwargs):
+        super().__init__(**kwargs)
+        self.c_puct = c_puct
+        self.temperature = temperature
+
+    def _search_kwargs(self):
+        return {"c_puct": self.c_puct}
+
+    def _mcts(self, legal_actions, state):
+        if self.temperature is not None and self.temperature > 1.0e-12:
+            raise NotImplementedError                 # as mcts.py:318-323
+        return super()._mcts(legal_actions, state)

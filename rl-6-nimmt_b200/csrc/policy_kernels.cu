@@ -13,128 +13,9 @@
 //   softmax over each decision's legal slots, probabilities out.
 // Hidden width 100 is padded to 112 (tcgen05 N granularity 16 at M = 128); padded weights are zero.
 // Features are built on chip from int8 observations, so the GEMMs never read activations from HBM.
-#include "abi_common.cuh"
-#include "tcgen05.cuh"
-
-#include <cuda_bf16.h>
+#include "policy_tile.cuh"
 
 namespace nimmt {
-
-constexpr int kIn = 48, kHid = 100, kHidPad = 112, kObs = 47;
-constexpr int kTileRows = 128, kSlots = 10, kDecPerTile = 12;
-constexpr int kInChunks = kIn / 8, kHidChunks = kHidPad / 8;
-constexpr uint32_t kW1Bytes = (kHidPad / 8) * kInChunks * 128;    // 10752
-constexpr uint32_t kW2Bytes = (kHidPad / 8) * kHidChunks * 128;   // 25088
-constexpr uint32_t kOffW1 = 0, kOffW2 = kOffW1 + kW1Bytes, kOffB1 = kOffW2 + kW2Bytes, kOffB2 = kOffB1 + kHidPad * 4;
-constexpr uint32_t kOffW3 = kOffB2 + kHidPad * 4, kOffB3 = kOffW3 + kHidPad * 4, kBlobBytes = kOffB3 + 16;   // 37200
-constexpr uint32_t kA1Bytes = (kTileRows / 8) * kInChunks * 128;  // 12288
-constexpr uint32_t kA2Bytes = (kTileRows / 8) * kHidChunks * 128; // 28672
-constexpr uint32_t kSmemBlob = 0, kSmemA1 = (kBlobBytes + 127) / 128 * 128, kSmemA2 = kSmemA1 + kA1Bytes;
-constexpr uint32_t kSmemLogits = kSmemA2 + kA2Bytes, kSmemTotal = kSmemLogits + kTileRows * 4;
-constexpr uint32_t kTmemCols = 128;
-
-// segments of the 48-vector [action, obs47] and their normalisation ranges (preprocessing.py:21-47)
-struct Segment { int begin, end; float lo, hi; };
-static const Segment kSegments[7] = {{0, 1, 0, 103}, {1, 11, 0, 103}, {11, 12, 0, 6}, {12, 16, 1, 5}, {16, 20, 0, 103}, {20, 24, 1, 10}, {24, 48, 0, 103}};
-
-static uint16_t float_to_bf16_rne(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);   // inf / nan: truncate
-    u += 0x7FFFu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
-
-// One 128-row tile through the three layers.  All 128 threads call this together.
-//   a1: the tile's raw features in canonical K-major layout (written by the caller)
-//   logit: this thread's row
-__device__ __forceinline__ float mlp_tile(uint8_t* smem, uint32_t tmem_base, uint64_t* bar, uint32_t& phase) {
-    const int row = threadIdx.x, warp = threadIdx.x >> 5;
-    const uint32_t a1 = smem_u32(smem + kSmemA1), a2 = smem_u32(smem + kSmemA2);
-    const uint32_t w1 = smem_u32(smem + kSmemBlob + kOffW1), w2 = smem_u32(smem + kSmemBlob + kOffW2);
-    const float* b1 = reinterpret_cast<const float*>(smem + kSmemBlob + kOffB1);
-    const float* b2 = reinterpret_cast<const float*>(smem + kSmemBlob + kOffB2);
-    const float* w3 = reinterpret_cast<const float*>(smem + kSmemBlob + kOffW3);
-    const float b3 = *reinterpret_cast<const float*>(smem + kSmemBlob + kOffB3);
-    constexpr uint32_t idesc = umma_idesc_bf16(kTileRows, kHidPad);
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-
-    // ---- layer 1 ----
-    fence_async_smem();          // the caller's feature stores -> visible to the tensor-core (async) proxy
-    tc_fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        tc_fence_after_sync();
-#pragma unroll
-        for (int ks = 0; ks < kIn / 16; ++ks)
-            umma_bf16(tmem_base, umma_desc(a1 + ks * 256, 128, kInChunks * 128), umma_desc(w1 + ks * 256, 128, kInChunks * 128), idesc, ks > 0);
-        umma_commit(bar);
-    }
-    mbar_wait_or_trap(bar, phase);
-    phase ^= 1u;
-    tc_fence_after_sync();
-    // epilogue 1: + b1, ReLU, round to bf16, store as layer 2's A operand
-#pragma unroll
-    for (int c = 0; c < kHidPad / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld16(lane_taddr + c * 16, v);
-        tmem_ld_wait();
-        uint32_t packed[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float x0 = fmaxf(__uint_as_float(v[2 * i]) + b1[c * 16 + 2 * i], 0.0f);
-            const float x1 = fmaxf(__uint_as_float(v[2 * i + 1]) + b1[c * 16 + 2 * i + 1], 0.0f);
-            const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-            packed[i] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        uint8_t* dst = smem + kSmemA2 + canon_off(row, c * 16, kHidChunks);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-    }
-    // ---- layer 2 ----
-    fence_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();             // every lane's accumulator has been read: TMEM may be overwritten
-    if (threadIdx.x == 0) {
-        tc_fence_after_sync();
-#pragma unroll
-        for (int ks = 0; ks < kHidPad / 16; ++ks)
-            umma_bf16(tmem_base, umma_desc(a2 + ks * 256, 128, kHidChunks * 128), umma_desc(w2 + ks * 256, 128, kHidChunks * 128), idesc, ks > 0);
-        umma_commit(bar);
-    }
-    mbar_wait_or_trap(bar, phase);
-    phase ^= 1u;
-    tc_fence_after_sync();
-    // epilogue 2 + layer 3: logit = w3 . relu(acc + b2) + b3, fp32
-    float logit = b3;
-#pragma unroll
-    for (int c = 0; c < kHidPad / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld16(lane_taddr + c * 16, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) logit = fmaf(fmaxf(__uint_as_float(v[i]) + b2[c * 16 + i], 0.0f), w3[c * 16 + i], logit);
-    }
-    tc_fence_before_sync();      // ordered before the caller's next __syncthreads / next tile's MMA
-    return logit;
-}
-
-// Writes one feature row [card | obs47] as bf16 into the layer-1 A operand.
-__device__ __forceinline__ void write_feature_row(uint8_t* smem, int row, int card, const int8_t* obs /*47, or nullptr for a zero row*/) {
-#pragma unroll
-    for (int c = 0; c < kInChunks; ++c) {
-        uint32_t packed[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k0 = c * 8 + 2 * i, k1 = k0 + 1;
-            const float x0 = obs ? (float)(k0 == 0 ? card : obs[k0 - 1]) : 0.0f;
-            const float x1 = obs ? (float)obs[k1 - 1] : 0.0f;
-            const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-            packed[i] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        *reinterpret_cast<uint4*>(smem + kSmemA1 + canon_off(row, c * 8, kInChunks)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    }
-}
 
 // grid-stride over tiles of 12 decisions.  obs: int8 [D][47]; probs: float [D][10] (0 for empty slots);
 // logits (optional): float [D][10].
@@ -165,7 +46,8 @@ k_policy_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
         const bool in_range = threadIdx.x < kDecPerTile * kSlots && dec < D;
         const int8_t* o = obs + dec * kObs;
         const int card = in_range ? o[slot] : -1;      // hand slot: the candidate card, -1 if empty (env.py:209-210)
-        write_feature_row(smem, threadIdx.x, card, (in_range && card >= 0) ? o : nullptr);
+        const bool live = in_range && card >= 0;
+        write_feature_row(smem, threadIdx.x, [&](int k) -> float { return live ? (float)(k == 0 ? card : o[k - 1]) : 0.0f; });
 
         const float logit = mlp_tile(smem, tmem_base, &bar, phase);
 

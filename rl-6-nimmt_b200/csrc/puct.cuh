@@ -1,0 +1,76 @@
+// puct.cuh — PUCTAgent's root rule (agents/mcts.py:276-315), __host__ __device__ so that the CPU
+// tests can check it against vectors generated from the reference.
+//
+//   puct_a = q_hat_a + c_puct * pi_a * sqrt(N + 1e-9) / (1 + n_a)                       (:301)
+//   q_hat  = clip((q - min) / (max - min), 0, 1),  q_a = mean outcome of a, or "mean" if unvisited (:299-300)
+//   (max, min, "mean") = (0, -10, -5) while fewer than 10 outcomes exist, else the max, min and
+//   MEDIAN of all outcomes so far                                                        (:304-315)
+//   choice = first index with the strictly largest puct; NaNs never win, so when every outcome is equal
+//   (0/0) the first card is chosen                                                        (:286-293)
+// Outcomes are integers in [-171, 0]; their multiset is kept as a histogram of magnitudes.
+#pragma once
+#include <cstdint>
+#include "game.cuh"
+
+namespace nimmt {
+
+constexpr int kOutcomeBins = 172;   // bull heads in the deck: 171
+
+struct RootStats {
+    int count[10];
+    int sum[10];          // sum of outcomes (<= 0)
+    long long sumsq[10];
+    uint16_t hist[kOutcomeBins];   // hist[m] = number of outcomes equal to -m
+    int total;
+};
+
+NIMMT_HD void root_stats_clear(RootStats& s) {
+    for (int a = 0; a < 10; ++a) { s.count[a] = 0; s.sum[a] = 0; s.sumsq[a] = 0; }
+    for (int m = 0; m < kOutcomeBins; ++m) s.hist[m] = 0;
+    s.total = 0;
+}
+
+NIMMT_HD void root_stats_add(RootStats& s, int action_index, int outcome) {
+    s.count[action_index] += 1;
+    s.sum[action_index] += outcome;
+    s.sumsq[action_index] += (long long)outcome * outcome;
+    s.hist[-outcome] += 1;
+    s.total += 1;
+}
+
+// k-th smallest outcome (0-based) of the multiset: scan magnitudes from the largest down.
+NIMMT_HD int kth_smallest_outcome(const RootStats& s, int k) {
+    int seen = 0;
+    for (int m = kOutcomeBins - 1; m >= 0; --m) {
+        seen += s.hist[m];
+        if (seen > k) return -m;
+    }
+    return 0;
+}
+
+// Returns the index (into the n legal cards, ascending) PUCT selects; pucts[] receives the values.
+NIMMT_HD int puct_choose(const RootStats& s, const float* probs, int n, float c_puct, double* pucts) {
+    double mx, mn, md;
+    if (s.total < 10) {
+        mx = 0.0; mn = -10.0; md = -5.0;
+    } else {
+        mn = (double)kth_smallest_outcome(s, 0);
+        mx = (double)kth_smallest_outcome(s, s.total - 1);
+        md = 0.5 * ((double)kth_smallest_outcome(s, (s.total - 1) / 2) + (double)kth_smallest_outcome(s, s.total / 2));   // np.median
+    }
+    const double root_n = sqrt((double)s.total + 1.0e-9);
+    int choice = 0;
+    double best = -INFINITY;
+    for (int a = 0; a < n; ++a) {
+        const double q = s.count[a] > 0 ? (double)s.sum[a] / (double)s.count[a] : md;
+        double qn = (q - mn) / (mx - mn);          // 0/0 -> NaN when all outcomes are equal: kept
+        qn = qn < 0.0 ? 0.0 : (qn > 1.0 ? 1.0 : qn);   // np.clip; NaN compares false twice and passes through
+        const float cp = c_puct * probs[a];        // float32 product first, as numpy does (python float * float32 array)
+        const double p = qn + (double)cp * root_n / (1.0 + (double)s.count[a]);
+        if (pucts) pucts[a] = p;
+        if (p > best) { best = p; choice = a; }
+    }
+    return choice;
+}
+
+}  // namespace nimmt

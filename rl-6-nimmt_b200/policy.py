@@ -28,6 +28,30 @@ class PolicyNet(nn.Module):
         return [head(latent) for head in self.head_nets]
 
 
+# (begin, end, min, max) of the segments of [action, obs47] (utils/preprocessing.py:21-47)
+_SEGMENTS = ((0, 1, 0.0, 103.0), (1, 11, 0.0, 103.0), (11, 12, 0.0, 6.0), (12, 16, 1.0, 5.0), (16, 20, 0.0, 103.0),
+             (20, 24, 1.0, 10.0), (24, 48, 0.0, 103.0))
+
+
+def normalize_rows(rows):
+    """SechsNimmtStateNormalization(action=True).forward (utils/preprocessing.py:12-57) in torch (training path)."""
+    scale = torch.empty(48, dtype=rows.dtype, device=rows.device)
+    shift = torch.empty(48, dtype=rows.dtype, device=rows.device)
+    for a, b, lo, hi in _SEGMENTS:
+        scale[a:b] = 2.0 / (hi - lo)
+        shift[a:b] = -1.0 - 2.0 * lo / (hi - lo)
+    return rows * scale + shift
+
+
+def torch_policy(net, state, legal_actions):
+    """PolicyMCSAgent._compute_policy (agents/mcts.py:219-228) with autograd: probabilities over the legal cards."""
+    state = torch.as_tensor(state, dtype=torch.float32).reshape(-1)
+    cards = torch.tensor([float(a) for a in legal_actions], dtype=torch.float32).unsqueeze(1)
+    rows = torch.cat((cards, state.unsqueeze(0).expand(len(legal_actions), -1)), dim=1)
+    (logits,) = net(normalize_rows(rows))
+    return torch.softmax(logits, dim=0).flatten()
+
+
 def pack_weights(net, device=None):
     """Packs a PolicyNet (or anything with the same state_dict keys) into the device blob."""
     lib = N.lib()

@@ -82,6 +82,27 @@ def mcs_rollouts(roots, num_players, rollouts_per_action, seed=0, rank=0, world=
     return out
 
 
+def policy_rollouts(roots, num_players, weights, n_mc, c_puct=2.0, root_rule=N.ROOT_PUCT, seed=0, device=None):
+    """Launches nimmt_policy_rollouts (PolicyMCSAgent / PUCTAgent searches, one per root).
+    Returns (stats int64 [D,10,3], root_probs float32 [D,10]) on the device."""
+    if not torch.cuda.is_available():
+        raise N.NimmtNativeError("policy_rollouts needs a CUDA device; there is no CPU fallback")
+    lib = N.lib()
+    device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    if not isinstance(roots, torch.Tensor):
+        roots = torch.as_tensor(np.ascontiguousarray(roots, dtype=np.uint8))
+    roots = roots.to(device).contiguous()
+    assert roots.dtype == torch.uint8 and roots.dim() == 2 and roots.shape[1] == ROOT_BYTES
+    D = roots.shape[0]
+    stats = torch.zeros((D, MAX_ACTIONS, 3), dtype=torch.int64, device=device)
+    probs = torch.zeros((D, MAX_ACTIONS), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        N.check(lib.nimmt_policy_rollouts(N.ptr(roots), D, int(num_players), N.ptr(weights), int(n_mc), float(c_puct), int(root_rule),
+                                          int(seed) & (2**64 - 1), N.ptr(stats), N.ptr(probs),
+                                          torch.cuda.current_stream(device).cuda_stream), "nimmt_policy_rollouts")
+    return stats, probs
+
+
 def sharded_mcs_rollouts(roots, num_players, rollouts_per_action, seed=0, group=None, device=None):
     """One decision batch spread over all ranks of the process group: stripe, play, all-reduce."""
     import torch.distributed as dist

@@ -19,6 +19,8 @@ Outputs (all under tests/golden/, all small, all committed):
   mcs_exact.json       exact E[outcome | first card] by exhaustive enumeration through
                        the reference env for small roots (KAT-C and friends), and
                        reference-MCSAgent Monte-Carlo estimates for z-tests.
+  policy_rollouts.npz  reference PolicyMCSAgent rollouts with a sharpened policy: per-first-card outcome
+                       mean / variance / count, the root policy, the weights, the root.
   policy_vectors.npz   MultiHeadedMLP(48,(100,100),(1,)) weights (torch.manual_seed(0)),
                        input rows, SechsNimmtStateNormalization outputs, softmax probs,
                        and PUCTAgent._compute_pucts / _normalize_q vectors.
@@ -478,7 +480,50 @@ def make_policy_vectors():
     return out, cases
 
 
+def make_policy_rollouts(n_rollouts=2500):
+    """Reference PolicyMCSAgent rollouts (agents/mcts.py:91-154, 209-228) with a SHARPENED policy
+    (head weights x 20, so that the policy is far from uniform and policy bugs would show) from a
+    4-player mid-game root: per first card the mean / variance / count of the outcomes."""
+    import torch
+    torch.manual_seed(0)
+    agent = ref.mcts.PolicyMCSAgent(mc_max=n_rollouts, mc_per_card=n_rollouts)
+    with torch.no_grad():
+        agent.actor.head_nets[0][0].weight *= 20.0
+    np.random.seed(21)
+    env = Env(4, verbose=False)
+    states, legal = env.reset()
+    for t in range(4):
+        (states, legal), _, _, _ = env.step([int(np.random.choice(l)) for l in legal])
+    state = torch.tensor(states[0], dtype=torch.float)
+    legal0 = list(map(int, legal[0]))
+    agent._initialize_game(state)
+    agent._memorize_cards(state, legal0)
+    root_probs = agent._compute_policy(legal0, state).detach().numpy()
+    np.random.seed(22)
+    torch.manual_seed(23)
+    outcomes = {a: [] for a in legal0}
+    for _ in range(n_rollouts):
+        e = agent._draw_env(legal0, state)
+        a, _, out = agent._play_out(e, outcomes)
+        outcomes[int(a)].append(float(out))
+    sd = {k: v.detach().numpy().copy() for k, v in agent.state_dict().items()}
+    out = {"w_" + k.replace(".", "_"): v for k, v in sd.items()}
+    out["state"] = np.array(states[0], np.int64)
+    out["legal"] = np.array(legal0, np.int64)
+    out["available"] = np.array(sorted(map(int, agent.available_cards)), np.int64)
+    out["root_probs"] = root_probs.astype(np.float32)
+    out["mean"] = np.array([np.mean(outcomes[a]) if outcomes[a] else np.nan for a in legal0])
+    out["var"] = np.array([np.var(outcomes[a]) if outcomes[a] else np.nan for a in legal0])
+    out["count"] = np.array([len(outcomes[a]) for a in legal0], np.int64)
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-policy-rollouts":
+        pr = make_policy_rollouts()
+        np.savez_compressed(os.path.join(HERE, "policy_rollouts.npz"), **pr)
+        print("policy rollouts:", dict(zip(pr["legal"].tolist(), zip(pr["mean"].round(3).tolist(), pr["count"].tolist()))), pr["root_probs"].round(3))
+        return
     games = parse_notebook_games()
     assert len(games) == 5, len(games)
     n_pen = replay_check_notebook(games)
@@ -506,6 +551,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "policy_vectors.npz"), **pol)
     json.dump(puct_cases, open(os.path.join(HERE, "puct_cases.json"), "w"), separators=(",", ":"))
     print("policy rows", pol["rows_in"].shape)
+    pr = make_policy_rollouts()
+    np.savez_compressed(os.path.join(HERE, "policy_rollouts.npz"), **pr)
 
 
 if __name__ == "__main__":

@@ -15,7 +15,7 @@ def lib():
     if _lib is None:
         src = os.path.join(_HERE, "host_sim.cu")
         csrc = os.path.join(_HERE, "..", "..", "rl-6-nimmt_b200", "csrc")
-        newest = max(os.path.getmtime(p) for p in [src] + [os.path.join(csrc, f) for f in ("game.cuh", "step.cuh", "rollout.cuh")])
+        newest = max(os.path.getmtime(p) for p in [src] + [os.path.join(csrc, f) for f in ("game.cuh", "step.cuh", "rollout.cuh", "puct.cuh")])
         if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
             subprocess.check_call(["nvcc", "-O1", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
                                    "-Wno-deprecated-gpu-targets", "-o", _LIB, src])
@@ -67,3 +67,17 @@ def mcs(P, root_bytes, rollouts, seed, rank=0, world=1):
     rc = lib().sim_mcs(P, buf, ctypes.c_int64(rollouts), ctypes.c_uint64(seed), rank, world, _p(stats))
     assert rc == 0, rc
     return stats
+
+
+def puct(legal, outcomes, probs, c_puct=2.0):
+    """outcomes: dict card -> list of outcomes. Returns (choice index, pucts float64[n])."""
+    idx, out = [], []
+    for i, a in enumerate(legal):
+        for o in outcomes[a]:
+            idx.append(i)
+            out.append(int(o))
+    idx, out = np.array(idx, np.int32), np.array(out, np.int32)
+    probs = np.ascontiguousarray(probs, np.float32)
+    pucts = np.zeros(len(legal), np.float64)
+    choice = lib().sim_puct(len(legal), len(out), _p(idx), _p(out), _p(probs), ctypes.c_float(c_puct), _p(pucts))
+    return choice, pucts

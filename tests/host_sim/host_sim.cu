@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstring>
 
+#include "../../rl-6-nimmt_b200/csrc/puct.cuh"
 #include "../../rl-6-nimmt_b200/csrc/rollout.cuh"
 #include "../../rl-6-nimmt_b200/csrc/step.cuh"
 
@@ -135,6 +136,13 @@ static int mcs(const nimmt_root& root, int64_t R, uint64_t seed, int rank, int w
 }
 
 extern "C" {
+// PUCT root rule on explicit outcome lists: (action index, outcome) pairs in visiting order.
+int sim_puct(int n, int n_outcomes, const int* action_index, const int* outcome, const float* probs, float c_puct, double* pucts) {
+    RootStats s;
+    root_stats_clear(s);
+    for (int i = 0; i < n_outcomes; ++i) root_stats_add(s, action_index[i], outcome[i]);
+    return puct_choose(s, probs, n, c_puct, pucts);
+}
 int sim_mcs(int P_, const nimmt_root* root, int64_t R, uint64_t seed, int rank, int world, int64_t* stats) {
     DISPATCH(P_, return mcs<P>(*root, R, seed, rank, world, stats));
     return 0;

@@ -74,3 +74,111 @@ def test_torch_module_is_state_dict_compatible():
     rows = torch.from_numpy(z["rows_norm"])
     (logit,) = net(rows)
     np.testing.assert_allclose(logit.detach().numpy().reshape(-1), z["logits"], rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# policy rollouts (PolicyMCSAgent / PUCTAgent searches on chip)
+# ---------------------------------------------------------------------------------------------------
+import oracle  # noqa: E402
+from rl_6_nimmt_b200 import _native as N  # noqa: E402
+from rl_6_nimmt_b200 import rollouts as R  # noqa: E402
+
+
+def _rollout_golden():
+    z = np.load(os.path.join(GOLDEN, "policy_rollouts.npz"))
+    net = PL.PolicyNet()
+    net.load_state_dict({k[len("w_actor_"):].replace("latent_net_0_", "latent_net.0.").replace("latent_net_2_", "latent_net.2.")
+                         .replace("head_nets_0_0_", "head_nets.0.0."): torch.from_numpy(z[k]) for k in z.files if k.startswith("w_actor_")})
+    w = {"w1": z["w_actor_latent_net_0_weight"], "b1": z["w_actor_latent_net_0_bias"], "w2": z["w_actor_latent_net_2_weight"],
+         "b2": z["w_actor_latent_net_2_bias"], "w3": z["w_actor_head_nets_0_0_weight"], "b3": z["w_actor_head_nets_0_0_bias"]}
+    return z, net, w
+
+
+def test_policy_rollouts_vs_reference_and_oracle():
+    """Sharpened policy, 4-player mid-game root.  Stratified root (equal budget per card): per-card means
+    z-tested (|z| < 4.5) against the unmodified reference's PolicyMCSAgent rollouts and against the fp32
+    C oracle; root policy within 1e-3 of the reference's."""
+    z, net, w = _rollout_golden()
+    legal, avail = z["legal"].tolist(), z["available"].tolist()
+    root = R.pack_root_from_state(z["state"], legal, avail)
+    blob = PL.pack_weights(net)
+    n_mc = 6 * 20_000
+    stats, probs = R.policy_rollouts(root[None], 4, blob, n_mc, root_rule=N.ROOT_STRATIFIED, seed=7)
+    stats, probs = stats[0].cpu().numpy(), probs[0].cpu().numpy()
+    assert np.abs(probs[:6] - z["root_probs"]).max() < 1e-3 and (probs[6:] == 0).all()
+    board = [[int(c) for c in row if c >= 0] for row in z["state"][-24:].reshape(4, 6)]
+    want = oracle.policy_rollouts(4, board, legal, avail, 30_000, w, seed=5)
+    for i, a in enumerate(legal):
+        s, ss, n = (int(x) for x in stats[i])
+        assert n == 20_000
+        mean, var = s / n, ss / n - (s / n) ** 2
+        zr = (mean - z["mean"][i]) / np.sqrt(var / n + z["var"][i] / z["count"][i])
+        ws, wss, wn = (int(x) for x in want[i])
+        wmean, wvar = ws / wn, wss / wn - (ws / wn) ** 2
+        zo = (mean - wmean) / np.sqrt(var / n + wvar / wn)
+        assert abs(zr) < 4.5 and abs(zo) < 4.5, (a, mean, z["mean"][i], wmean, zr, zo)
+        assert abs(var - wvar) < 0.15 * wvar
+    assert (stats[6:] == 0).all()
+
+
+def test_policy_root_rule_follows_the_policy():
+    z, net, w = _rollout_golden()
+    legal = z["legal"].tolist()
+    root = R.pack_root_from_state(z["state"], legal, z["available"].tolist())
+    blob = PL.pack_weights(net)
+    n_mc = 60_000
+    stats, probs = R.policy_rollouts(root[None], 4, blob, n_mc, root_rule=N.ROOT_POLICY, seed=11)
+    counts = stats[0, :6, 2].cpu().numpy()
+    assert counts.sum() == n_mc
+    assert np.abs(counts / n_mc - z["root_probs"]).max() < 5 * np.sqrt(0.2 / n_mc) + 1e-3
+
+
+def test_puct_search_batch():
+    """256 trees at once (BASELINE configs[3] shape): every tree spends exactly n_mc rollouts, visits
+    concentrate on the better cards, and equal roots with different tree ids give different searches."""
+    z, net, w = _rollout_golden()
+    legal = z["legal"].tolist()
+    root = R.pack_root_from_state(z["state"], legal, z["available"].tolist())
+    blob = PL.pack_weights(net)
+    roots = np.repeat(root[None], 256, axis=0)
+    stats, probs = R.policy_rollouts(roots, 4, blob, 200, c_puct=2.0, root_rule=N.ROOT_PUCT, seed=3)
+    stats = stats.cpu().numpy()
+    assert (stats[:, :6, 2].sum(axis=1) == 200).all() and (stats[:, 6:] == 0).all()
+    assert len({tuple(s[:6, 2]) for s in stats}) > 100                  # different seeds per tree
+    visits = stats[:, :6, 2].mean(axis=0)
+    # cards 82 / 87 (indices 4, 5) are clearly best at this root (reference: -7.0 vs -9 .. -10)
+    assert visits[4] + visits[5] > visits[:4].sum() * 0.6, visits
+    means = stats[:, :6, 0].sum(axis=0) / stats[:, :6, 2].sum(axis=0)
+    assert np.argmax(means) in (4, 5)
+    # PUCT prior phase: with fewer than 10 outcomes q_hat uses (0,-10,-5); first visit goes to the highest prior
+    s1, _ = R.policy_rollouts(roots[:3], 4, blob, 1, root_rule=N.ROOT_PUCT, seed=3)
+    assert (s1[:, int(np.argmax(z["root_probs"])), 2] == 1).all()
+
+
+def test_alpha05_agent_dropin_plays_and_learns():
+    from rl_6_nimmt_b200.agents import DrunkHamster, PUCTAgent
+    from rl_6_nimmt_b200.env import SechsNimmtEnv
+    torch.manual_seed(0)
+    np.random.seed(1)
+    agent = PUCTAgent(mc_max=60, seed=2)
+    agent.train()
+    before = [p.detach().clone() for p in agent.parameters()]
+    agents = [agent, DrunkHamster(), DrunkHamster()]
+    env = SechsNimmtEnv(3, verbose=False)
+    states, legal = env.reset()
+    done, rewards = False, np.zeros(3, np.int32)
+    while not done:                                   # the reference's GameSession loop (play.py:23-75)
+        acts, infos = [], []
+        for ag, s, l in zip(agents, states, legal):
+            a, info = ag(torch.tensor(s, dtype=torch.float), legal_actions=l)
+            acts.append(int(a)); infos.append(info)
+        (nstates, nlegal), nrew, done, _ = env.step(acts)
+        for ag, a, s, ns, r, nr, info, l, nl in zip(agents, acts, states, nstates, rewards, nrew, infos, legal, nlegal):
+            ag.learn(state=s, legal_actions=list(l), reward=r, action=a, done=done, next_state=ns, next_legal_actions=list(nl),
+                     next_reward=nr, num_episode=0, episode_end=done, **info)
+        states, legal, rewards = nstates, nlegal, nrew
+    assert agent.last_stats[:, 2].sum() >= 20        # last search (2 cards): min(mc_max, 10 * 2!) = 20 rollouts
+    assert any(not torch.equal(b, p.detach()) for b, p in zip(before, agent.parameters()))   # one Adam step happened
+    key = agent._packed_key
+    agent._weights()
+    assert agent._packed_key != key                    # weights were repacked after the update

@@ -78,3 +78,23 @@ def test_root_rejects_short_pool():
     stats = np.zeros((10, 3), np.int64)
     buf = (ctypes.c_uint8 * 64).from_buffer_copy(root.tobytes())
     assert lib().sim_mcs(3, buf, ctypes.c_int64(10), ctypes.c_uint64(1), 0, 1, _p(stats)) == -2
+
+
+def test_puct_rule_matches_reference_cases():
+    """puct.cuh (the code the rollout kernel runs at the root) against PUCTAgent._compute_pucts /
+    _normalize_q vectors generated from the reference, including <10 outcomes => (0,-10,-5), the
+    median rule, and the all-equal 0/0 => NaN => first card case."""
+    from host_sim import puct
+    cases = json.load(open(os.path.join(GOLDEN, "puct_cases.json")))
+    n_nan = 0
+    for c in cases:
+        outcomes = {int(a): o for a, o in c["outcomes"].items()}
+        choice, pucts = puct(c["legal"], outcomes, c["probs"])
+        for got, want in zip(pucts, c["pucts"]):
+            if want is None:
+                assert np.isnan(got)
+                n_nan += 1
+            else:
+                assert abs(got - want) < 1e-12, (got, want)
+        assert choice == c["choice"]
+    assert n_nan > 0

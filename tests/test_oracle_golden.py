@@ -220,3 +220,26 @@ def test_puct_oracle():
                 assert abs(got - want) < 1e-9
         assert po.puct_choice(p) == c["choice"]
     assert n_nan > 0  # the 0/0 case (all outcomes equal) is covered
+
+
+def test_policy_rollout_oracle_vs_reference():
+    """The fp32 C restatement of PolicyMCSAgent rollouts agrees with the unmodified reference (sharpened
+    policy, 4-player mid-game root): z-test per first card, and first-card frequencies ~ root policy."""
+    z = np.load(os.path.join(GOLDEN, "policy_rollouts.npz"))
+    w = {"w1": z["w_actor_latent_net_0_weight"], "b1": z["w_actor_latent_net_0_bias"], "w2": z["w_actor_latent_net_2_weight"],
+         "b2": z["w_actor_latent_net_2_bias"], "w3": z["w_actor_head_nets_0_0_weight"], "b3": z["w_actor_head_nets_0_0_bias"]}
+    board = [[int(c) for c in row if c >= 0] for row in z["state"][-24:].reshape(4, 6)]
+    legal, avail = z["legal"].tolist(), z["available"].tolist()
+    N = 25_000
+    stats = oracle.policy_rollouts(4, board, legal, avail, N, w, seed=3)
+    assert stats[:, 2].sum() == N
+    for i, a in enumerate(legal):
+        s, ss, n = (int(x) for x in stats[i])
+        mean, var = s / n, ss / n - (s / n) ** 2
+        zscore = (mean - z["mean"][i]) / np.sqrt(var / n + z["var"][i] / z["count"][i])
+        assert abs(zscore) < 4.5, (a, mean, z["mean"][i], zscore)
+        assert abs(n / N - z["root_probs"][i]) < 5 * np.sqrt(z["root_probs"][i] / N) + 1e-3
+    # the policy matters: uniform-random rollouts from the same root give different values for some card
+    uni = oracle.mcs_rollouts(4, board, legal, avail, N, seed=4)
+    diffs = [abs(stats[i, 0] / stats[i, 2] - uni[i, 0] / uni[i, 2]) for i in range(len(legal))]
+    assert max(diffs) > 0.15, diffs
