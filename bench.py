@@ -388,6 +388,43 @@ def run_ours(args):
         mcs_ms = float(t.item())
     mcs_value = world * reps * 256 * 10 * per_action / (mcs_ms * 1e-3)
 
+    # ---- Alpha0.5 (BASELINE configs[3]): 256 PUCT searches per GPU, 200 rollouts each, policy net on tcgen05 ----
+    from rl_6_nimmt_b200 import policy as PL
+    torch.manual_seed(0)
+    blob = PL.pack_weights(PL.PolicyNet(), device=dev)
+    R.policy_rollouts(roots_d, P, blob, 200, seed=1)
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for r in range(3):
+        R.policy_rollouts(roots_d, P, blob, 200, seed=2 + r)
+    a1.record()
+    barrier()
+    puct_ms = a0.elapsed_time(a1) / 3
+    # batched leaf evaluation: the policy for every seat of 2^18 games (2^20 decisions, ~8.9e6 rows of 48 features)
+    obs_all = envs[0].reset(seed=77).observe(dtype=torch.int8).reshape(-1, 47)[: 1 << 20].contiguous()
+    PL.policy_probs(obs_all, blob)
+    barrier()
+    a0.record()
+    for r in range(3):
+        PL.policy_probs(obs_all, blob)
+    a1.record()
+    barrier()
+    leaf_ms = a0.elapsed_time(a1) / 3
+    if world > 1:
+        t = torch.tensor([puct_ms, leaf_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        puct_ms, leaf_ms = float(t[0]), float(t[1])
+    rows_per_rollout = P * sum(range(1, 11))           # 220 policy rows in a full 4-player rollout
+    flop_per_row = 2 * (48 * 100 + 100 * 100 + 100)    # un-padded, SURVEY.md §8d
+    alpha = {
+        "puct_rollouts_per_sec": world * 256 * 200 / (puct_ms * 1e-3), "ms_per_256_decisions": puct_ms,
+        "config": "256 PUCT searches per GPU (4-player opening roots, 10 legal cards), 200 sequential rollouts each, random-init policy net (torch.manual_seed(0))",
+        "policy_tflops_in_search": world * 256 * 200 * rows_per_rollout * flop_per_row / (puct_ms * 1e-3) / 1e12,
+        "leaf_eval_decisions_per_sec": world * (1 << 20) / (leaf_ms * 1e-3),
+        "leaf_eval_tflops": world * float((obs_all[:, :10] >= 0).sum()) * flop_per_row / (leaf_ms * 1e-3) / 1e12,
+    }
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -417,6 +454,7 @@ def run_ours(args):
         "also": {"k_random_actions_ms": ra_ms, "k_deal_ms": deal_ms,
                  "fused_random_play_env_steps_per_sec": world * B / (fused_ms * 1e-3),
                  "fused_note": "k_step<4,true>: actions drawn in-kernel, + k_deal every 10th visit; per-rank ms, not max-reduced"},
+        "alpha05": alpha,
         "mcs": {"metric": "mcs_rollouts_per_sec", "value": mcs_value, "unit": "rollouts/s",
                 "config": "256 four-player opening roots x 10 candidate cards x 2000 rollouts per launch, 5 launches"},
     }

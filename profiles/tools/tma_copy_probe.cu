@@ -4,6 +4,7 @@
 // and 32- vs 128-game tiles.  Built and run by hand:
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I rl-6-nimmt_b200/csrc -o /tmp/probe profiles/tools/tma_copy_probe.cu
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <vector>
 #include "tma.cuh"
@@ -87,16 +88,16 @@ float run(const char* name, int64_t total_bytes, int nsets) {
     return ms;
 }
 
-int main() {
-    const int64_t total = 92LL << 20;   // bytes moved each way per launch, like k_step<4> on 2^20 games (88 + 4)
-    const int nsets = 4;
+int main(int argc, char** argv) {
+    const int64_t total = (argc > 1 ? atoll(argv[1]) : 92LL) << 20;   // bytes moved each way per launch, like k_step<4> on 2^20 games (88 + 4)
+    const int nsets = argc > 2 ? atoi(argv[2]) : 4;
     {   // reference: plain copy
-        uint4 *a[4], *b[4];
+        uint4 *a[8], *b[8];
         for (int s = 0; s < nsets; ++s) { cudaMalloc(&a[s], total); cudaMalloc(&b[s], total); cudaMemset(a[s], 1, total); }
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-        for (int i = 0; i < 4; ++i) k_plain<<<148 * 8, 256>>>(a[i % 4], b[i % 4], total / 16);
+        for (int i = 0; i < 4; ++i) k_plain<<<148 * 8, 256>>>(a[i % nsets], b[i % nsets], total / 16);
         cudaEventRecord(e0);
-        for (int i = 0; i < 40; ++i) k_plain<<<148 * 8, 256>>>(a[i % 4], b[i % 4], total / 16);
+        for (int i = 0; i < 40; ++i) k_plain<<<148 * 8, 256>>>(a[i % nsets], b[i % nsets], total / 16);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 40;
         printf("%-34s : %.2f us  %.0f GB/s (read+write)\n", "plain uint4 grid-stride copy", ms * 1e3, 2.0 * total / (ms * 1e-3) / 1e9);
