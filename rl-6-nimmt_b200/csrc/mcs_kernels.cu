@@ -25,11 +25,41 @@ k_mcs_rollouts(const nimmt_root* __restrict__ roots, int64_t local_rollouts, int
     if (threadIdx.x < 16) reinterpret_cast<uint32_t*>(&root)[threadIdx.x] = reinterpret_cast<const uint32_t*>(roots + d)[threadIdx.x];
     __syncthreads();
 
-    uint4 own, pool;
-    BoardLite board;
-    if (!decode_root<P>(root, values, own, pool, board)) return;  // whole block; stats stay zero
-    if (a >= mask_count(own)) return;
-    const int first = (int)mask_select(own, (uint32_t)a);
+    __shared__ RolloutRoot rr;
+    __shared__ int root_ok;
+    __shared__ __align__(4) uint8_t decks[kMcsThreads * kRolloutDeckStride];
+    // cooperative version of make_rollout_root (rollout.cuh): thread c places card c at its rank in the
+    // ascending pool / own lists, so building the 116-byte record costs ~20 instructions per thread
+    {
+        __shared__ uint4 s_own, s_pool;
+        if (threadIdx.x == 0) {
+            uint4 own, pool;
+            root_ok = decode_root<P>(root, values, own, pool, rr.board) ? 1 : 0;
+            s_own = own; s_pool = pool;
+            rr.n_pool = mask_count(pool);
+            rr.n_own = mask_count(own);
+        }
+        if (threadIdx.x < kRolloutDeckStride / 4) reinterpret_cast<uint32_t*>(rr.deck)[threadIdx.x] = 0u;
+        __syncthreads();
+        const uint32_t c = threadIdx.x;
+        if (c < (uint32_t)kCards) {
+            const uint32_t word = c >> 5, below_bits = (1u << (c & 31)) - 1u;
+            auto rank_in = [&](const uint4& m) -> int {   // number of set cards below c
+                const uint32_t w0 = m.x, w1 = m.y, w2 = m.z, w3 = m.w & kHighCardMask;
+                int n = 0;
+                n += word > 0 ? __popc(w0) : __popc(w0 & below_bits);
+                if (word >= 1) n += word > 1 ? __popc(w1) : __popc(w1 & below_bits);
+                if (word >= 2) n += word > 2 ? __popc(w2) : __popc(w2 & below_bits);
+                if (word >= 3) n += __popc(w3 & below_bits);
+                return n;
+            };
+            if (mask_has(s_pool, c)) rr.deck[rank_in(s_pool)] = (uint8_t)c;
+            if (mask_has(s_own, c)) rr.deck[kOwnOffset + rank_in(s_own)] = (uint8_t)c;
+        }
+    }
+    __syncthreads();
+    if (!root_ok || a >= rr.n_own) return;   // whole block; stats stay zero
+    uint8_t* deck = decks + threadIdx.x * kRolloutDeckStride;
 
     long long s = 0, ss = 0, cnt = 0;
     const int64_t base = ((int64_t)blockIdx.x * iters) * kMcsThreads + threadIdx.x;
@@ -38,7 +68,7 @@ k_mcs_rollouts(const nimmt_root* __restrict__ roots, int64_t local_rollouts, int
         if (i < local_rollouts) {
             const uint64_t j = (uint64_t)rank + (uint64_t)i * (uint64_t)world;
             const uint64_t id = ((uint64_t)d << 44) | ((uint64_t)a << 40) | j;
-            const int out = rollout<P>(own, pool, board, first, values, seed, id);
+            const int out = rollout<P>(rr, a, values, deck, seed, id);
             s += out; ss += (long long)out * out; cnt += 1;
         }
     }

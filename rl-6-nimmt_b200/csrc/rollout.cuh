@@ -49,15 +49,50 @@ NIMMT_HD bool decode_root(const nimmt_root& root, const uint8_t* values, uint4& 
     return root.num_players == P && mask_count(pool) >= (P - 1) * mask_count(own);
 }
 
-// Plays one rollout.  `own` = the deciding player's hand, `pool` = cards the agent believes unseen
-// (BaseMCAgent.available_cards), `first` = the card forced as player 0's first move (stratified
-// root: the caller runs the same number of rollouts for every legal card).  Returns the outcome
-// (sum of player 0's rewards, <= 0).  Requires |pool| >= (P-1) |own|.
+// Root position as the rollouts consume it: the unseen cards and the own hand as byte lists (one
+// 116-byte record: 104 pool slots, 10 own slots, 2 pad — copied into each thread's private scratch at
+// the start of every rollout), plus the row keys.
+constexpr int kRolloutDeckStride = 116;   // 29 words: odd word stride => private decks never share a bank per index
+constexpr int kOwnOffset = 104;
+
+struct RolloutRoot {
+    alignas(4) uint8_t deck[kRolloutDeckStride];
+    int n_pool, n_own;
+    BoardLite board;
+};
+
 template <int P>
-NIMMT_HD int rollout(uint4 own, uint4 pool, BoardLite board, int first, const uint8_t* values, uint64_t seed, uint64_t rollout_id) {
+NIMMT_HD bool make_rollout_root(const nimmt_root& root, const uint8_t* values, RolloutRoot& rr) {
+    uint4 own, pool;
+    if (!decode_root<P>(root, values, own, pool, rr.board)) return false;
+    int n = 0;
+    for (int c = 0; c < kCards; ++c)
+        if (mask_has(pool, (uint32_t)c)) rr.deck[n++] = (uint8_t)c;
+    rr.n_pool = n;
+    for (int i = n; i < kOwnOffset; ++i) rr.deck[i] = 0;
+    n = 0;
+    for (int c = 0; c < kCards; ++c)
+        if (mask_has(own, (uint32_t)c)) rr.deck[kOwnOffset + n++] = (uint8_t)c;
+    rr.n_own = n;
+    for (int i = kOwnOffset + n; i < kRolloutDeckStride; ++i) rr.deck[i] = 0;
+    return true;
+}
+
+// Plays one rollout.  `first_index` = rank (ascending) of the card forced as player 0's first move
+// (stratified root: the caller runs the same number of rollouts for every legal card).  `deck` is 116
+// bytes of scratch private to the caller.  Cards are drawn by partial Fisher-Yates: the opponents'
+// P-1 cards per turn from the pool prefix, player 0's card by swap-remove from its own list — a few
+// shared-memory byte accesses per draw instead of a popcount search through a 104-bit mask.
+// Returns the outcome (sum of player 0's rewards, <= 0).  Depends on (seed, rollout_id) only.
+template <int P>
+NIMMT_HD int rollout(const RolloutRoot& rr, int first_index, const uint8_t* values, uint8_t* deck, uint64_t seed, uint64_t rollout_id) {
+#pragma unroll
+    for (int w = 0; w < kRolloutDeckStride / 4; ++w) reinterpret_cast<uint32_t*>(deck)[w] = reinterpret_cast<const uint32_t*>(rr.deck)[w];
     Philox rng(seed, rollout_id, /*stream=*/0x6d637300u, 0);
-    int n_own = mask_count(own);
-    uint32_t n_pool = (uint32_t)mask_count(pool);
+    BoardLite board = rr.board;
+    int n_own = rr.n_own;
+    uint32_t drawn = 0;
+    const uint32_t n_pool = (uint32_t)rr.n_pool;
     int outcome = 0;
     uint4 r = make_uint4(0, 0, 0, 0);
     int used = 4;
@@ -73,16 +108,18 @@ NIMMT_HD int rollout(uint4 own, uint4 pool, BoardLite board, int first, const ui
         // player 0: forced card on the first turn, uniform afterwards (mcts.py:140-145, 187-188)
         {
             const uint32_t w = next_word();
-            const int card = first_turn ? first : (int)mask_select(own, below(w, (uint32_t)n_own));
-            mask_clear(own, (uint32_t)card);
+            const uint32_t idx = first_turn ? (uint32_t)first_index : below(w, (uint32_t)n_own);
+            const int card = deck[kOwnOffset + idx];
             --n_own;
+            deck[kOwnOffset + idx] = deck[kOwnOffset + n_own];   // swap-remove
             keys[0] = card << 4;
         }
 #pragma unroll
         for (int p = 1; p < P; ++p) {
-            const uint32_t card = mask_select(pool, below(next_word(), n_pool));
-            mask_clear(pool, card);
-            --n_pool;
+            const uint32_t j = drawn + below(next_word(), n_pool - drawn);
+            const uint32_t card = deck[j];
+            deck[j] = deck[drawn];   // position `drawn` is never read again: half a swap suffices
+            ++drawn;
             keys[p] = (int)(card << 4) | p;
         }
         sort_keys<P>(keys);

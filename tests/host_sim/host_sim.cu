@@ -120,15 +120,14 @@ static int check_network() {
 
 template <int P>
 static int mcs(const nimmt_root& root, int64_t R, uint64_t seed, int rank, int world, int64_t* stats) {
-    uint4 own, pool;
-    BoardLite board;
-    if (!decode_root<P>(root, h_card_value, own, pool, board)) return -2;
-    const int n = mask_count(own);
+    RolloutRoot rr;
+    if (!make_rollout_root<P>(root, h_card_value, rr)) return -2;
+    alignas(4) uint8_t deck[kRolloutDeckStride];
+    const int n = rr.n_own;
     for (int a = 0; a < n; ++a) {
-        const int first = (int)mask_select(own, a);
         for (int64_t j = rank; j < R; j += world) {
             const uint64_t id = ((uint64_t)a << 40) | (uint64_t)j;  // root index d = 0
-            const int out = rollout<P>(own, pool, board, first, h_card_value, seed, id);
+            const int out = rollout<P>(rr, a, h_card_value, deck, seed, id);
             stats[a * 3 + 0] += out; stats[a * 3 + 1] += (int64_t)out * out; stats[a * 3 + 2] += 1;
         }
     }
