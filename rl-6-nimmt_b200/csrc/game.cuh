@@ -74,11 +74,14 @@ struct Philox {
         k[0] = (uint32_t)seed;
         k[1] = (uint32_t)(seed >> 32);
     }
-    // Returns 4 fresh 32-bit words and advances the block counter.
+    // Returns 4 fresh 32-bit words and advances the block counter.  ROUNDS = 10 is the standard
+    // generator; 7 is the smallest round count that still passes BigCrush (Salmon et al. 2011, table 2)
+    // and is used where the RNG is a large share of the work (rollouts).
+    template <int ROUNDS = 10>
     NIMMT_HD uint4 next() {
         uint32_t x0 = c[0], x1 = c[1], x2 = c[2], x3 = c[3], k0 = k[0], k1 = k[1];
 #pragma unroll
-        for (int r = 0; r < 10; ++r) {
+        for (int r = 0; r < ROUNDS; ++r) {
             const uint32_t lo0 = 0xD2511F53u * x0, hi0 = umulhi32(0xD2511F53u, x0);
             const uint32_t lo1 = 0xCD9E8D57u * x2, hi1 = umulhi32(0xCD9E8D57u, x2);
             x0 = hi1 ^ x1 ^ k0;

@@ -105,12 +105,13 @@ int nimmt_mcs_rollouts(const nimmt_root* roots, int num_roots, int num_players, 
     if ((reinterpret_cast<uintptr_t>(roots) & 15u) || (reinterpret_cast<uintptr_t>(stats) & 7u)) return NIMMT_E_ALIGN;
     const int64_t local = rollouts_per_action > rank ? (rollouts_per_action - rank + world - 1) / world : 0;
     if (num_roots == 0 || local == 0) return NIMMT_OK;
-    // rollouts per thread: enough blocks to fill 148 SMs several times over, few enough atomics
+    // rollouts per thread: aim for ~6 resident waves of blocks (each block pays a root decode and three
+    // barriers), then shrink `iters` to the smallest value that still covers `local` with that many chunks
     const int64_t total_threads = local * 10 * (int64_t)num_roots;
-    int iters = (int)(total_threads / ((int64_t)kMcsThreads * 148 * 32));
-    iters = iters < 1 ? 1 : iters > 64 ? 64 : iters;
-    const int64_t per_block = (int64_t)kMcsThreads * iters;
-    const int64_t chunks = (local + per_block - 1) / per_block;
+    int64_t target = total_threads / ((int64_t)kMcsThreads * 148 * 3 * 6);
+    target = target < 1 ? 1 : target > 64 ? 64 : target;
+    const int64_t chunks = (local + kMcsThreads * target - 1) / (kMcsThreads * target);
+    const int iters = (int)((local + kMcsThreads * chunks - 1) / (kMcsThreads * chunks));
     if (chunks > 0x7FFFFFFF) return NIMMT_E_BADARG;
     dim3 grid((unsigned)chunks, 10, (unsigned)num_roots);
     unsigned long long* st = reinterpret_cast<unsigned long long*>(stats);

@@ -97,7 +97,7 @@ NIMMT_HD int rollout(const RolloutRoot& rr, int first_index, const uint8_t* valu
     uint4 r = make_uint4(0, 0, 0, 0);
     int used = 4;
     auto next_word = [&]() -> uint32_t {
-        if (used == 4) { r = rng.next(); used = 0; }
+        if (used == 4) { r = rng.next<7>(); used = 0; }
         const uint32_t w = used == 0 ? r.x : used == 1 ? r.y : used == 2 ? r.z : r.w;
         ++used;
         return w;

@@ -88,7 +88,7 @@ NIMMT_HD void deal_game(Game<P>& g, uint64_t seed, uint64_t game_id, const uint8
     for (int i = 0; i < kCards / 4; ++i) reinterpret_cast<uint32_t*>(deck)[i] = 0x03020100u + 0x04040404u * (uint32_t)i;
     uint4 r = make_uint4(0, 0, 0, 0);
     auto draw = [&](int i) -> uint32_t {
-        if ((i & 3) == 0) r = rng.next();
+        if ((i & 3) == 0) r = rng.next<7>();
         const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
         const uint32_t j = (uint32_t)i + below(word, (uint32_t)(kCards - i));
         const uint32_t card = deck[j];
@@ -117,7 +117,7 @@ NIMMT_HD void random_actions_game(const Game<P>& g, uint64_t seed, uint64_t game
     uint4 r = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        if ((p & 3) == 0) r = rng.next();
+        if ((p & 3) == 0) r = rng.next<7>();
         const uint32_t word = (p & 3) == 0 ? r.x : (p & 3) == 1 ? r.y : (p & 3) == 2 ? r.z : r.w;
         const uint32_t n = (uint32_t)mask_count(g.hand[p]);
         act[p] = n ? (int)mask_select(g.hand[p], below(word, n)) : 255;
