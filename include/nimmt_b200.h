@@ -150,6 +150,22 @@ typedef struct nimmt_root {
 NIMMT_API int nimmt_mcs_rollouts(const nimmt_root *roots, int num_roots, int num_players, int64_t rollouts_per_action,
                                  uint64_t seed, int rank, int world, int64_t *stats, void *stream);
 
+/* ---- batched Monte-Carlo agents (the bookkeeping BaseMCAgent does on the host, for B games at once) ---- */
+
+/* BaseMCAgent._initialize_game / _memorize_cards / _board_from_state (agents/mcts.py:62-89) for the agent at
+ * `seat` of every game: available[b] (one 128-bit card mask per game, caller-owned, uint4 [B]) loses the
+ * seat's hand and every card lying on the board now (with `initialize` != 0 it first becomes the full
+ * deck, as at the start of a game, agents/mcts.py:47-48); then roots[b] is written for nimmt_mcs_rollouts /
+ * nimmt_policy_rollouts.  Call once per decision, before the step, exactly as the agent's forward() runs. */
+NIMMT_API int nimmt_mc_roots(const void *state, void *available, nimmt_root *roots, int64_t num_games, int num_players,
+                             int seat, int initialize, void *stream);
+
+/* BaseMCAgent._choose_action_from_outcomes (agents/mcts.py:156-165) and the single-card shortcut (:52-53):
+ * actions[b][seat] = the legal card with the largest mean outcome in stats int64 [B][10][3] (strict '>' in
+ * ascending card order; cards without rollouts never win).  Other seats' bytes of `actions` are untouched. */
+NIMMT_API int nimmt_mc_choose(const void *state, const int64_t *stats, uint8_t *actions, int64_t num_games, int num_players,
+                              int seat, void *stream);
+
 /* ---- Alpha0.5 leaf evaluation (the only dense GEMM on the path; tcgen05 tensor cores) ---- */
 
 /* Bytes of the packed policy-weight blob consumed by the kernels below. */

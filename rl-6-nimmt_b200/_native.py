@@ -46,6 +46,8 @@ SIGNATURES = {
     "nimmt_random_actions": (_int, [_vp, _vp, _i64, _int, _u64, _u32, _u64, _vp]),
     "nimmt_step_random": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _u64, _u32, _u64, _vp]),
     "nimmt_mcs_rollouts": (_int, [_vp, _int, _int, _i64, _u64, _int, _int, _vp, _vp]),
+    "nimmt_mc_roots": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
+    "nimmt_mc_choose": (_int, [_vp, _vp, _vp, _i64, _int, _int, _vp]),
     "nimmt_policy_weights_bytes": (ctypes.c_size_t, []),
     "nimmt_policy_pack_weights": (_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_float, _vp]),
     "nimmt_policy_probs": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),

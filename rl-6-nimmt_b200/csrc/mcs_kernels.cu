@@ -98,9 +98,18 @@ extern "C" {
 
 int nimmt_mcs_rollouts(const nimmt_root* roots, int num_roots, int num_players, int64_t rollouts_per_action, uint64_t seed,
                        int rank, int world, int64_t* stats, void* stream) {
-    if (!roots || !stats || num_roots < 0 || num_roots > 65535 || rollouts_per_action < 0 || world < 1 || rank < 0 ||
-        rank >= world || num_players < 1 || num_players > kMaxPlayers)
+    if (!roots || !stats || num_roots < 0 || rollouts_per_action < 0 || world < 1 || rank < 0 || rank >= world || num_players < 1 ||
+        num_players > kMaxPlayers)
         return NIMMT_E_BADARG;
+    if (num_roots > 32768) {   // grid.z limit: split the batch (roots are independent; ids keep the global root index out of the RNG key only per chunk)
+        for (int first = 0; first < num_roots; first += 32768) {
+            const int n = num_roots - first < 32768 ? num_roots - first : 32768;
+            const int rc = nimmt_mcs_rollouts(roots + first, n, num_players, rollouts_per_action, seed + 0x9E3779B97F4A7C15ull * (uint64_t)(first / 32768 + 1),
+                                              rank, world, stats + (int64_t)first * 30, stream);
+            if (rc) return rc;
+        }
+        return NIMMT_OK;
+    }
     if (rollouts_per_action >= ((int64_t)1 << 40)) return NIMMT_E_BADARG;
     if ((reinterpret_cast<uintptr_t>(roots) & 15u) || (reinterpret_cast<uintptr_t>(stats) & 7u)) return NIMMT_E_ALIGN;
     const int64_t local = rollouts_per_action > rank ? (rollouts_per_action - rank + world - 1) / world : 0;
