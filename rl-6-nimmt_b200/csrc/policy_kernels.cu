@@ -24,6 +24,7 @@ k_policy_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) int8_t tile_obs[kDecPerTile * kObs + 4];
 
     for (uint32_t i = threadIdx.x * 16; i < kBlobBytes; i += kTileRows * 16)
         *reinterpret_cast<uint4*>(smem + kSmemBlob + i) = *reinterpret_cast<const uint4*>(blob + i);
@@ -44,7 +45,19 @@ k_policy_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
         const int dec_local = threadIdx.x / kSlots, slot = threadIdx.x % kSlots;
         const int64_t dec = tile * kDecPerTile + dec_local;
         const bool in_range = threadIdx.x < kDecPerTile * kSlots && dec < D;
-        const int8_t* o = obs + dec * kObs;
+        // stage the tile's 12 x 47 observation bytes with coalesced 4-byte loads (564 B, 4-byte aligned)
+        {
+            const int64_t first_byte = tile * (kDecPerTile * kObs), total_bytes = D * kObs;
+            for (int wd = threadIdx.x; wd < kDecPerTile * kObs / 4; wd += kTileRows) {
+                const int64_t byte = first_byte + 4 * wd;
+                uint32_t v = 0;
+                if (byte + 4 <= total_bytes) v = *reinterpret_cast<const uint32_t*>(obs + byte);
+                else for (int i = 0; i < 4; ++i) if (byte + i < total_bytes) v |= (uint32_t)(uint8_t)obs[byte + i] << (8 * i);
+                reinterpret_cast<uint32_t*>(tile_obs)[wd] = v;
+            }
+        }
+        __syncthreads();
+        const int8_t* o = tile_obs + dec_local * kObs;
         const int card = in_range ? o[slot] : -1;      // hand slot: the candidate card, -1 if empty (env.py:209-210)
         const bool live = in_range && card >= 0;
         write_feature_row(smem, threadIdx.x, [&](int k) -> float { return live ? (float)(k == 0 ? card : o[k - 1]) : 0.0f; });

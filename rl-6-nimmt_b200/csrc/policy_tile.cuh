@@ -35,6 +35,13 @@ static inline uint16_t float_to_bf16_rne(float f) {
     return (uint16_t)(u >> 16);
 }
 
+// max(x, 0) rounded to bf16, two at a time, in one instruction (x1 lands in the upper half).
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float x0, float x1) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x1), "f"(x0));
+    return d;
+}
+
 // One 128-row tile through the three layers.  All 128 threads call this together.
 //   a1: the tile's raw features in canonical K-major layout (written by the caller)
 //   logit: this thread's row
@@ -63,23 +70,23 @@ __device__ __forceinline__ float mlp_tile(uint8_t* smem, uint32_t tmem_base, uin
     mbar_wait_or_trap(bar, phase);
     phase ^= 1u;
     tc_fence_after_sync();
-    // epilogue 1: + b1, ReLU, round to bf16, store as layer 2's A operand
+    // epilogue 1: + b1, ReLU, round to bf16, store as layer 2's A operand.  All seven 16-column TMEM
+    // loads are issued before the single wait, so their latencies overlap.
+    {
+        uint32_t v[kHidPad / 16][16];
 #pragma unroll
-    for (int c = 0; c < kHidPad / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld16(lane_taddr + c * 16, v);
+        for (int c = 0; c < kHidPad / 16; ++c) tmem_ld16(lane_taddr + c * 16, v[c]);
         tmem_ld_wait();
-        uint32_t packed[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float x0 = fmaxf(__uint_as_float(v[2 * i]) + b1[c * 16 + 2 * i], 0.0f);
-            const float x1 = fmaxf(__uint_as_float(v[2 * i + 1]) + b1[c * 16 + 2 * i + 1], 0.0f);
-            const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-            packed[i] = *reinterpret_cast<const uint32_t*>(&h);
+        for (int c = 0; c < kHidPad / 16; ++c) {
+            uint32_t packed[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                packed[i] = relu_pack_bf16x2(__uint_as_float(v[c][2 * i]) + b1[c * 16 + 2 * i], __uint_as_float(v[c][2 * i + 1]) + b1[c * 16 + 2 * i + 1]);
+            uint8_t* dst = smem + kSmemA2 + canon_off(row, c * 16, kHidChunks);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            *reinterpret_cast<uint4*>(dst + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
         }
-        uint8_t* dst = smem + kSmemA2 + canon_off(row, c * 16, kHidChunks);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
     }
     // ---- layer 2 ----
     fence_async_smem();
@@ -97,13 +104,18 @@ __device__ __forceinline__ float mlp_tile(uint8_t* smem, uint32_t tmem_base, uin
     tc_fence_after_sync();
     // epilogue 2 + layer 3: logit = w3 . relu(acc + b2) + b3, fp32
     float logit = b3;
+    {
+        uint32_t v[kHidPad / 16][16];
 #pragma unroll
-    for (int c = 0; c < kHidPad / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld16(lane_taddr + c * 16, v);
+        for (int c = 0; c < kHidPad / 16; ++c) tmem_ld16(lane_taddr + c * 16, v[c]);
         tmem_ld_wait();
+        float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // four independent accumulation chains
 #pragma unroll
-        for (int i = 0; i < 16; ++i) logit = fmaf(fmaxf(__uint_as_float(v[i]) + b2[c * 16 + i], 0.0f), w3[c * 16 + i], logit);
+        for (int c = 0; c < kHidPad / 16; ++c)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                part[i & 3] = fmaf(fmaxf(__uint_as_float(v[c][i]) + b2[c * 16 + i], 0.0f), w3[c * 16 + i], part[i & 3]);
+        logit += (part[0] + part[1]) + (part[2] + part[3]);
     }
     tc_fence_before_sync();      // ordered before the caller's next __syncthreads / next tile's MMA
     return logit;
