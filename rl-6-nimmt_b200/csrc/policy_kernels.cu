@@ -17,38 +17,42 @@
 
 namespace nimmt {
 
-// grid-stride over tiles of 12 decisions.  obs: int8 [D][47]; probs: float [D][10] (0 for empty slots);
-// logits (optional): float [D][10].
-__global__ void __launch_bounds__(kTileRows, 1)
+// grid-stride over tiles of 12 decisions; every 128-thread group of the CTA takes its own tiles.
+// obs: int8 [D][47]; probs: float [D][10] (0 for empty slots); logits (optional): float [D][10].
+// kProbGroups groups share one copy of the weights in shared memory and each own 128 TMEM columns, an
+// mbarrier and a named barrier, so one group's epilogue (TMEM -> registers -> bf16 -> shared memory)
+// runs under the other groups' MMAs.
+constexpr int kProbGroups = 4;
+__global__ void __launch_bounds__(kTileRows * kProbGroups, 1)
 k_policy_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restrict__ blob, float* __restrict__ probs, float* __restrict__ logits) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[kProbGroups];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) int8_t tile_obs[kDecPerTile * kObs + 4];
 
-    for (uint32_t i = threadIdx.x * 16; i < kBlobBytes; i += kTileRows * 16)
+    for (uint32_t i = threadIdx.x * 16; i < kBlobBytes; i += blockDim.x * 16)
         *reinterpret_cast<uint4*>(smem + kSmemBlob + i) = *reinterpret_cast<const uint4*>(blob + i);
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_barrier_init();
-    }
-    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, kTmemCols);
+    if (threadIdx.x < kProbGroups) mbar_init(&bars[threadIdx.x], 1);
+    if (threadIdx.x == 0) fence_barrier_init();
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, kTmemColsPerGroup * kProbGroups);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_slot;
+    const int group = threadIdx.x / kTileRows, tid = threadIdx.x % kTileRows, bar_id = 1 + group;
+    const uint32_t tmem_base = tmem_slot + group * kTmemColsPerGroup;
+    uint8_t* gbuf = smem + kSmemGroups + group * kGroupBytes;
     uint32_t phase = 0;
-    float* tile_logits = reinterpret_cast<float*>(smem + kSmemLogits);
+    float* tile_logits = reinterpret_cast<float*>(gbuf + kGLogits);
+    int8_t* tile_obs = reinterpret_cast<int8_t*>(gbuf + kGObs);
 
     const int64_t num_tiles = (D + kDecPerTile - 1) / kDecPerTile;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int dec_local = threadIdx.x / kSlots, slot = threadIdx.x % kSlots;
+    for (int64_t tile = (int64_t)blockIdx.x * kProbGroups + group; tile < num_tiles; tile += (int64_t)gridDim.x * kProbGroups) {
+        const int dec_local = tid / kSlots, slot = tid % kSlots;
         const int64_t dec = tile * kDecPerTile + dec_local;
-        const bool in_range = threadIdx.x < kDecPerTile * kSlots && dec < D;
+        const bool in_range = tid < kDecPerTile * kSlots && dec < D;
         // stage the tile's 12 x 47 observation bytes with coalesced 4-byte loads (564 B, 4-byte aligned)
         {
             const int64_t first_byte = tile * (kDecPerTile * kObs), total_bytes = D * kObs;
-            for (int wd = threadIdx.x; wd < kDecPerTile * kObs / 4; wd += kTileRows) {
+            for (int wd = tid; wd < kDecPerTile * kObs / 4; wd += kTileRows) {
                 const int64_t byte = first_byte + 4 * wd;
                 uint32_t v = 0;
                 if (byte + 4 <= total_bytes) v = *reinterpret_cast<const uint32_t*>(obs + byte);
@@ -56,16 +60,16 @@ k_policy_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
                 reinterpret_cast<uint32_t*>(tile_obs)[wd] = v;
             }
         }
-        __syncthreads();
+        group_sync(bar_id);
         const int8_t* o = tile_obs + dec_local * kObs;
         const int card = in_range ? o[slot] : -1;      // hand slot: the candidate card, -1 if empty (env.py:209-210)
         const bool live = in_range && card >= 0;
-        write_feature_row(smem, threadIdx.x, [&](int k) -> float { return live ? (float)(k == 0 ? card : o[k - 1]) : 0.0f; });
+        write_feature_row(gbuf, tid, [&](int k) -> float { return live ? (float)(k == 0 ? card : o[k - 1]) : 0.0f; });
 
-        const float logit = mlp_tile(smem, tmem_base, &bar, phase);
+        const float logit = mlp_tile(smem + kSmemBlob, gbuf, tmem_base, &bars[group], phase, tid, bar_id);
 
-        tile_logits[threadIdx.x] = logit;
-        __syncthreads();
+        tile_logits[tid] = logit;
+        group_sync(bar_id);
         if (in_range) {
             // softmax over the decision's legal slots (agents/mcts.py:207,227: Softmax(dim=0) over the rows)
             float m = -INFINITY;
@@ -77,11 +81,11 @@ k_policy_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
             probs[dec * kSlots + slot] = card >= 0 ? __expf(logit - m) / z : 0.0f;
             if (logits) logits[dec * kSlots + slot] = card >= 0 ? logit : 0.0f;
         }
-        __syncthreads();   // tile_logits and the A operands are free again
+        group_sync(bar_id);   // tile_logits, tile_obs and the A operands are free again
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem_base, kTmemCols);
+    if (threadIdx.x < 32) tmem_dealloc(tmem_slot, kTmemColsPerGroup * kProbGroups);
 }
 
 }  // namespace nimmt
@@ -132,11 +136,11 @@ int nimmt_policy_probs(const int8_t* obs, int64_t num_decisions, const void* wei
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_policy_probs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+        cudaFuncSetAttribute(k_policy_probs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)policy_smem_bytes(kProbGroups));
     }
-    const int64_t tiles = (num_decisions + kDecPerTile - 1) / kDecPerTile;
-    const unsigned blocks = (unsigned)(tiles < 2 * num_sms ? tiles : 2 * num_sms);
-    k_policy_probs<<<blocks, kTileRows, kSmemTotal, (cudaStream_t)stream>>>(obs, num_decisions, static_cast<const uint8_t*>(weights), probs, logits);
+    const int64_t tiles = (num_decisions + kDecPerTile - 1) / kDecPerTile, ctas = (tiles + kProbGroups - 1) / kProbGroups;
+    const unsigned blocks = (unsigned)(ctas < num_sms ? ctas : num_sms);   // persistent: one 4-group CTA per SM
+    k_policy_probs<<<blocks, kTileRows * kProbGroups, policy_smem_bytes(kProbGroups), (cudaStream_t)stream>>>(obs, num_decisions, static_cast<const uint8_t*>(weights), probs, logits);
     return check_launch();
 }
 

@@ -57,13 +57,14 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
-    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, kTmemCols);
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, kTmemColsPerGroup);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
     uint32_t phase = 0;
-    float* tile_logits = reinterpret_cast<float*>(smem + kSmemLogits);
+    uint8_t* gbuf = smem + kSmemGroups;
+    float* tile_logits = reinterpret_cast<float*>(gbuf + kGLogits);
 
     // thread roles
     const int dec = threadIdx.x / kSlots, slot = threadIdx.x % kSlots;      // row = (decision, hand slot)
@@ -158,7 +159,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
             // ---- features of every (tree, player, slot) row (env.py:174-212 layout behind the candidate card) ----
             const int card = playing ? ts.hand[player][slot] : -1;
             const bool live = playing && card >= 0;
-            write_feature_row(smem, threadIdx.x, [&](int k) -> float {
+            write_feature_row(gbuf, threadIdx.x, [&](int k) -> float {
                 if (!live) return 0.0f;
                 if (k == 0) return (float)card;
                 if (k <= 10) return (float)ts.hand[player][k - 1];
@@ -168,7 +169,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
                 if (k <= 23) return (float)ts.sum[k - 20];
                 return (float)ts.board[(k - 24) / 6][(k - 24) % 6];
             });
-            const float logit = mlp_tile(smem, tmem_base, &bar, phase);
+            const float logit = mlp_tile(smem + kSmemBlob, gbuf, tmem_base, &bar, phase, threadIdx.x, 0);
             tile_logits[threadIdx.x] = logit;
             __syncthreads();
 
@@ -250,7 +251,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem_base, kTmemCols);
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base, kTmemColsPerGroup);
 }
 
 }  // namespace nimmt
@@ -274,8 +275,8 @@ int nimmt_policy_rollouts(const nimmt_root* roots, int num_roots, int num_player
     switch (num_players) {
 #define CASE(P_)                                                                                                             \
     case P_:                                                                                                                 \
-        cudaFuncSetAttribute(k_policy_rollouts<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);            \
-        k_policy_rollouts<P_><<<blocks, kTileRows, kSmemTotal, cs>>>(roots, num_roots, blob, n_mc, c_puct, mode, seed, st, root_probs); \
+        cudaFuncSetAttribute(k_policy_rollouts<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)policy_smem_bytes(1));            \
+        k_policy_rollouts<P_><<<blocks, kTileRows, policy_smem_bytes(1), cs>>>(roots, num_roots, blob, n_mc, c_puct, mode, seed, st, root_probs); \
         break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
 #undef CASE

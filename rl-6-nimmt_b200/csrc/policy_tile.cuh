@@ -19,9 +19,16 @@ constexpr uint32_t kOffW1 = 0, kOffW2 = kOffW1 + kW1Bytes, kOffB1 = kOffW2 + kW2
 constexpr uint32_t kOffW3 = kOffB2 + kHidPad * 4, kOffB3 = kOffW3 + kHidPad * 4, kBlobBytes = kOffB3 + 16;   // 37200
 constexpr uint32_t kA1Bytes = (kTileRows / 8) * kInChunks * 128;  // 12288
 constexpr uint32_t kA2Bytes = (kTileRows / 8) * kHidChunks * 128; // 28672
-constexpr uint32_t kSmemBlob = 0, kSmemA1 = (kBlobBytes + 127) / 128 * 128, kSmemA2 = kSmemA1 + kA1Bytes;
-constexpr uint32_t kSmemLogits = kSmemA2 + kA2Bytes, kSmemTotal = kSmemLogits + kTileRows * 4;
-constexpr uint32_t kTmemCols = 128;
+// dynamic shared memory: the weight blob, then one buffer set per tile group (a group = 128 threads that
+// push tiles through the net independently of the other groups of the CTA, sharing only the weights)
+constexpr uint32_t kSmemBlob = 0, kSmemGroups = (kBlobBytes + 127) / 128 * 128;
+constexpr uint32_t kGA1 = 0, kGA2 = kGA1 + kA1Bytes, kGLogits = kGA2 + kA2Bytes, kGObs = kGLogits + kTileRows * 4;
+constexpr uint32_t kGroupBytes = (kGObs + kDecPerTile * kObs + 4 + 127) / 128 * 128;
+constexpr uint32_t kTmemColsPerGroup = 128;
+__host__ __device__ constexpr uint32_t policy_smem_bytes(int groups) { return kSmemGroups + (uint32_t)groups * kGroupBytes; }
+
+// Barrier over the 128 threads of one tile group (named barrier `id`; id 0 with a single group is __syncthreads).
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kTileRows) : "memory"); }
 
 // segments of the 48-vector [action, obs47] and their normalisation ranges (preprocessing.py:21-47)
 struct Segment { int begin, end; float lo, hi; };
@@ -42,25 +49,61 @@ __device__ __forceinline__ uint32_t relu_pack_bf16x2(float x0, float x1) {
     return d;
 }
 
-// One 128-row tile through the three layers.  All 128 threads call this together.
-//   a1: the tile's raw features in canonical K-major layout (written by the caller)
-//   logit: this thread's row
-__device__ __forceinline__ float mlp_tile(uint8_t* smem, uint32_t tmem_base, uint64_t* bar, uint32_t& phase) {
-    const int row = threadIdx.x, warp = threadIdx.x >> 5;
-    const uint32_t a1 = smem_u32(smem + kSmemA1), a2 = smem_u32(smem + kSmemA2);
-    const uint32_t w1 = smem_u32(smem + kSmemBlob + kOffW1), w2 = smem_u32(smem + kSmemBlob + kOffW2);
-    const float* b1 = reinterpret_cast<const float*>(smem + kSmemBlob + kOffB1);
-    const float* b2 = reinterpret_cast<const float*>(smem + kSmemBlob + kOffB2);
-    const float* w3 = reinterpret_cast<const float*>(smem + kSmemBlob + kOffW3);
-    const float b3 = *reinterpret_cast<const float*>(smem + kSmemBlob + kOffB3);
+// Epilogue 1 for hidden chunks [C0, C1) of 16 columns: TMEM -> + b1 -> ReLU -> bf16 -> layer 2's A operand.
+// The chunk's TMEM loads are all issued before the single wait, so their latencies overlap.
+template <int C0, int C1>
+__device__ __forceinline__ void epilogue1_chunks(uint32_t lane_taddr, const float* b1, uint8_t* a2_row) {
+    uint32_t v[C1 - C0][16];
+#pragma unroll
+    for (int c = C0; c < C1; ++c) tmem_ld16(lane_taddr + c * 16, v[c - C0]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = C0; c < C1; ++c) {
+        uint32_t packed[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            packed[i] = relu_pack_bf16x2(__uint_as_float(v[c - C0][2 * i]) + b1[c * 16 + 2 * i], __uint_as_float(v[c - C0][2 * i + 1]) + b1[c * 16 + 2 * i + 1]);
+        uint8_t* dst = a2_row + c * 256;   // canon_off(row, 16 c, .) = canon_off(row, 0, .) + 2 chunks of 128 B per c
+        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    }
+}
+
+// Epilogue 2 + layer 3 for hidden chunks [C0, C1): part += w3 . relu(acc + b2), four independent chains.
+template <int C0, int C1>
+__device__ __forceinline__ void epilogue2_chunks(uint32_t lane_taddr, const float* b2, const float* w3, float (&part)[4]) {
+    uint32_t v[C1 - C0][16];
+#pragma unroll
+    for (int c = C0; c < C1; ++c) tmem_ld16(lane_taddr + c * 16, v[c - C0]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = C0; c < C1; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            part[i & 3] = fmaf(fmaxf(__uint_as_float(v[c - C0][i]) + b2[c * 16 + i], 0.0f), w3[c * 16 + i], part[i & 3]);
+}
+
+// One 128-row tile through the three layers.  The 128 threads of a tile group call this together.
+//   blob: the weights; gbuf: the group's buffers, whose A1 operand the caller has filled with raw features
+//   in canonical K-major layout; tmem_base: the group's 128 accumulator columns; tid: 0..127 within the
+//   group; bar_id: the group's named barrier.  Returns this thread's row's logit.
+__device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, uint32_t tmem_base, uint64_t* bar, uint32_t& phase, int tid,
+                                          int bar_id) {
+    const int row = tid, warp = tid >> 5;
+    const uint32_t a1 = smem_u32(gbuf + kGA1), a2 = smem_u32(gbuf + kGA2);
+    const uint32_t w1 = smem_u32(blob + kOffW1), w2 = smem_u32(blob + kOffW2);
+    const float* b1 = reinterpret_cast<const float*>(blob + kOffB1);
+    const float* b2 = reinterpret_cast<const float*>(blob + kOffB2);
+    const float* w3 = reinterpret_cast<const float*>(blob + kOffW3);
+    const float b3 = *reinterpret_cast<const float*>(blob + kOffB3);
     constexpr uint32_t idesc = umma_idesc_bf16(kTileRows, kHidPad);
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 
     // ---- layer 1 ----
     fence_async_smem();          // the caller's feature stores -> visible to the tensor-core (async) proxy
     tc_fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    group_sync(bar_id);
+    if (tid == 0) {
         tc_fence_after_sync();
 #pragma unroll
         for (int ks = 0; ks < kIn / 16; ++ks)
@@ -70,29 +113,14 @@ __device__ __forceinline__ float mlp_tile(uint8_t* smem, uint32_t tmem_base, uin
     mbar_wait_or_trap(bar, phase);
     phase ^= 1u;
     tc_fence_after_sync();
-    // epilogue 1: + b1, ReLU, round to bf16, store as layer 2's A operand.  All seven 16-column TMEM
-    // loads are issued before the single wait, so their latencies overlap.
-    {
-        uint32_t v[kHidPad / 16][16];
-#pragma unroll
-        for (int c = 0; c < kHidPad / 16; ++c) tmem_ld16(lane_taddr + c * 16, v[c]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < kHidPad / 16; ++c) {
-            uint32_t packed[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                packed[i] = relu_pack_bf16x2(__uint_as_float(v[c][2 * i]) + b1[c * 16 + 2 * i], __uint_as_float(v[c][2 * i + 1]) + b1[c * 16 + 2 * i + 1]);
-            uint8_t* dst = smem + kSmemA2 + canon_off(row, c * 16, kHidChunks);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            *reinterpret_cast<uint4*>(dst + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-        }
-    }
+    // epilogue 1: + b1, ReLU, round to bf16, store as layer 2's A operand (4 + 3 chunks bound the live registers)
+    epilogue1_chunks<0, 4>(lane_taddr, b1, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
+    epilogue1_chunks<4, kHidPad / 16>(lane_taddr, b1, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
     // ---- layer 2 ----
     fence_async_smem();
     tc_fence_before_sync();
-    __syncthreads();             // every lane's accumulator has been read: TMEM may be overwritten
-    if (threadIdx.x == 0) {
+    group_sync(bar_id);          // every lane's accumulator has been read: TMEM may be overwritten
+    if (tid == 0) {
         tc_fence_after_sync();
 #pragma unroll
         for (int ks = 0; ks < kHidPad / 16; ++ks)
@@ -104,19 +132,10 @@ __device__ __forceinline__ float mlp_tile(uint8_t* smem, uint32_t tmem_base, uin
     tc_fence_after_sync();
     // epilogue 2 + layer 3: logit = w3 . relu(acc + b2) + b3, fp32
     float logit = b3;
-    {
-        uint32_t v[kHidPad / 16][16];
-#pragma unroll
-        for (int c = 0; c < kHidPad / 16; ++c) tmem_ld16(lane_taddr + c * 16, v[c]);
-        tmem_ld_wait();
-        float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // four independent accumulation chains
-#pragma unroll
-        for (int c = 0; c < kHidPad / 16; ++c)
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                part[i & 3] = fmaf(fmaxf(__uint_as_float(v[c][i]) + b2[c * 16 + i], 0.0f), w3[c * 16 + i], part[i & 3]);
-        logit += (part[0] + part[1]) + (part[2] + part[3]);
-    }
+    float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    epilogue2_chunks<0, 4>(lane_taddr, b2, w3, part);
+    epilogue2_chunks<4, kHidPad / 16>(lane_taddr, b2, w3, part);
+    logit += (part[0] + part[1]) + (part[2] + part[3]);
     tc_fence_before_sync();      // ordered before the caller's next __syncthreads / next tile's MMA
     return logit;
 }
@@ -124,7 +143,7 @@ __device__ __forceinline__ float mlp_tile(uint8_t* smem, uint32_t tmem_base, uin
 // Writes one 48-feature row as bf16 into the layer-1 A operand; feature(k) returns the raw value of
 // input k (k = 0: candidate card, k = 1..47: observation entry k - 1, env.py:174-212 layout).
 template <class F>
-__device__ __forceinline__ void write_feature_row(uint8_t* smem, int row, F feature) {
+__device__ __forceinline__ void write_feature_row(uint8_t* gbuf, int row, F feature) {
 #pragma unroll
     for (int c = 0; c < kInChunks; ++c) {
         uint32_t packed[4];
@@ -133,7 +152,7 @@ __device__ __forceinline__ void write_feature_row(uint8_t* smem, int row, F feat
             const __nv_bfloat162 h = __floats2bfloat162_rn(feature(c * 8 + 2 * i), feature(c * 8 + 2 * i + 1));
             packed[i] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        *reinterpret_cast<uint4*>(smem + kSmemA1 + canon_off(row, c * 8, kInChunks)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(gbuf + kGA1 + canon_off(row, c * 8, kInChunks)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
 }
 
