@@ -41,6 +41,7 @@ k_policy_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
     const uint32_t tmem_base = tmem_slot + group * kTmemColsPerGroup;
     uint8_t* gbuf = smem + kSmemGroups + group * kGroupBytes;
     uint32_t phase = 0;
+    PhaseClock pc;
     float* tile_logits = reinterpret_cast<float*>(gbuf + kGLogits);
     int8_t* tile_obs = reinterpret_cast<int8_t*>(gbuf + kGObs);
 
@@ -66,7 +67,7 @@ k_policy_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
         const bool live = in_range && card >= 0;
         write_feature_row(gbuf, tid, [&](int k) -> float { return live ? (float)(k == 0 ? card : o[k - 1]) : 0.0f; });
 
-        const float logit = mlp_tile(smem + kSmemBlob, gbuf, tmem_base, &bars[group], phase, tid, bar_id);
+        const float logit = mlp_tile(smem + kSmemBlob, gbuf, tmem_base, &bars[group], phase, tid, bar_id, pc);
 
         tile_logits[tid] = logit;
         group_sync(bar_id);

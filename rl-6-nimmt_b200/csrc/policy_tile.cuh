@@ -49,6 +49,27 @@ __device__ __forceinline__ uint32_t relu_pack_bf16x2(float x0, float x1) {
     return d;
 }
 
+// Bring-up instrument (-DNIMMT_PHASE_CLOCKS): thread 0 of block 0 accumulates clock64() deltas per phase
+// and prints them when the kernel ends.  Compiled out of the product build.
+struct PhaseClock {
+#ifdef NIMMT_PHASE_CLOCKS
+    long long acc[16] = {0}, last = 0;
+    __device__ __forceinline__ void start() { last = clock64(); }
+    __device__ __forceinline__ void mark(int i) {
+        const long long now = clock64();
+        acc[i] += now - last;
+        last = now;
+    }
+    __device__ void print(const char* const* names, int n) {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            for (int i = 0; i < n; ++i) printf("phase %-10s %12lld cycles\n", names[i], acc[i]);
+    }
+#else
+    __device__ __forceinline__ void start() {}
+    __device__ __forceinline__ void mark(int) {}
+#endif
+};
+
 // Epilogue 1 for hidden chunks [C0, C1) of 16 columns: TMEM -> + b1 -> ReLU -> bf16 -> layer 2's A operand.
 // The chunk's TMEM loads are all issued before the single wait, so their latencies overlap.
 template <int C0, int C1>
@@ -88,7 +109,7 @@ __device__ __forceinline__ void epilogue2_chunks(uint32_t lane_taddr, const floa
 //   in canonical K-major layout; tmem_base: the group's 128 accumulator columns; tid: 0..127 within the
 //   group; bar_id: the group's named barrier.  Returns this thread's row's logit.
 __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, uint32_t tmem_base, uint64_t* bar, uint32_t& phase, int tid,
-                                          int bar_id) {
+                                          int bar_id, PhaseClock& pc) {
     const int row = tid, warp = tid >> 5;
     const uint32_t a1 = smem_u32(gbuf + kGA1), a2 = smem_u32(gbuf + kGA2);
     const uint32_t w1 = smem_u32(blob + kOffW1), w2 = smem_u32(blob + kOffW2);
@@ -103,6 +124,7 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     fence_async_smem();          // the caller's feature stores -> visible to the tensor-core (async) proxy
     tc_fence_before_sync();
     group_sync(bar_id);
+    pc.mark(1);
     if (tid == 0) {
         tc_fence_after_sync();
 #pragma unroll
@@ -113,13 +135,16 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     mbar_wait_or_trap(bar, phase);
     phase ^= 1u;
     tc_fence_after_sync();
+    pc.mark(2);
     // epilogue 1: + b1, ReLU, round to bf16, store as layer 2's A operand (4 + 3 chunks bound the live registers)
     epilogue1_chunks<0, 4>(lane_taddr, b1, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
     epilogue1_chunks<4, kHidPad / 16>(lane_taddr, b1, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
     // ---- layer 2 ----
     fence_async_smem();
     tc_fence_before_sync();
+    pc.mark(3);
     group_sync(bar_id);          // every lane's accumulator has been read: TMEM may be overwritten
+    pc.mark(4);
     if (tid == 0) {
         tc_fence_after_sync();
 #pragma unroll
@@ -130,6 +155,7 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     mbar_wait_or_trap(bar, phase);
     phase ^= 1u;
     tc_fence_after_sync();
+    pc.mark(5);
     // epilogue 2 + layer 3: logit = w3 . relu(acc + b2) + b3, fp32
     float logit = b3;
     float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -137,6 +163,7 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     epilogue2_chunks<4, kHidPad / 16>(lane_taddr, b2, w3, part);
     logit += (part[0] + part[1]) + (part[2] + part[3]);
     tc_fence_before_sync();      // ordered before the caller's next __syncthreads / next tile's MMA
+    pc.mark(6);
     return logit;
 }
 

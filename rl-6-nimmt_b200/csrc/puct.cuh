@@ -22,12 +22,15 @@ struct RootStats {
     long long sumsq[10];
     uint16_t hist[kOutcomeBins];   // hist[m] = number of outcomes equal to -m
     int total;
+    int min_mag, max_mag;          // smallest / largest magnitude seen (= max / min outcome); valid when total > 0
 };
 
 NIMMT_HD void root_stats_clear(RootStats& s) {
     for (int a = 0; a < 10; ++a) { s.count[a] = 0; s.sum[a] = 0; s.sumsq[a] = 0; }
     for (int m = 0; m < kOutcomeBins; ++m) s.hist[m] = 0;
     s.total = 0;
+    s.min_mag = kOutcomeBins;
+    s.max_mag = -1;
 }
 
 NIMMT_HD void root_stats_add(RootStats& s, int action_index, int outcome) {
@@ -36,16 +39,22 @@ NIMMT_HD void root_stats_add(RootStats& s, int action_index, int outcome) {
     s.sumsq[action_index] += (long long)outcome * outcome;
     s.hist[-outcome] += 1;
     s.total += 1;
+    s.min_mag = -outcome < s.min_mag ? -outcome : s.min_mag;
+    s.max_mag = -outcome > s.max_mag ? -outcome : s.max_mag;
 }
 
-// k-th smallest outcome (0-based) of the multiset: scan magnitudes from the largest down.
-NIMMT_HD int kth_smallest_outcome(const RootStats& s, int k) {
-    int seen = 0;
-    for (int m = kOutcomeBins - 1; m >= 0; --m) {
+// np.median of the multiset of outcomes: mean of the two middle order statistics.  Outcomes cluster near
+// zero, so the scan runs over magnitudes from 0 upwards (k-th smallest outcome = (total - 1 - k)-th smallest
+// magnitude) and stops at the upper middle one, typically after a dozen bins.
+NIMMT_HD double median_outcome(const RootStats& s) {
+    const int k_lo = s.total - 1 - s.total / 2, k_hi = s.total - 1 - (s.total - 1) / 2;   // k_lo <= k_hi, magnitude ranks
+    int seen = 0, m_lo = -1;
+    for (int m = s.min_mag; m <= s.max_mag; ++m) {
         seen += s.hist[m];
-        if (seen > k) return -m;
+        if (m_lo < 0 && seen > k_lo) m_lo = m;
+        if (seen > k_hi) return -0.5 * ((double)m_lo + (double)m);
     }
-    return 0;
+    return 0.0;
 }
 
 // Returns the index (into the n legal cards, ascending) PUCT selects; pucts[] receives the values.
@@ -54,9 +63,9 @@ NIMMT_HD int puct_choose(const RootStats& s, const float* probs, int n, float c_
     if (s.total < 10) {
         mx = 0.0; mn = -10.0; md = -5.0;
     } else {
-        mn = (double)kth_smallest_outcome(s, 0);
-        mx = (double)kth_smallest_outcome(s, s.total - 1);
-        md = 0.5 * ((double)kth_smallest_outcome(s, (s.total - 1) / 2) + (double)kth_smallest_outcome(s, s.total / 2));   // np.median
+        mn = (double)-s.max_mag;
+        mx = (double)-s.min_mag;
+        md = median_outcome(s);   // np.median
     }
     const double root_n = sqrt((double)s.total + 1.0e-9);
     int choice = 0;
