@@ -95,7 +95,8 @@ def puct_choice(p):
 
 # ----------------------------------------------------------------------------------------------
 # Emulation of what the tcgen05 kernel computes, for sharp kernel tests: normalisation folded
-# into layer 1, bf16 operands, fp32 accumulation, hidden layer 1 rounded to bf16, layer 3 in fp32.
+# into layer 1, bf16 operands, fp32 accumulation, biases carried through the GEMMs as two bf16 terms
+# (hi + lo) against constant-1 inputs, hidden layer 1 rounded to bf16, layer 3 in fp32.
 # The fp32 functions above remain the reference semantics; this one only explains the rounding.
 # ----------------------------------------------------------------------------------------------
 def _bf16(x):
@@ -111,11 +112,16 @@ def fold_normalization(w):
     return (w1 * scale[None, :]).astype(np.float32), (w["b1"].astype(np.float64) + w1 @ shift).astype(np.float32)
 
 
+def _bf16_hi_lo(b):
+    hi = _bf16(b)
+    return hi + _bf16(np.asarray(b, np.float32) - hi)
+
+
 def policy_logits_bf16(rows, w):
     w1f, b1f = fold_normalization(w)
     x = _bf16(rows)                      # raw features are small integers: exact
-    h1 = np.maximum(x @ _bf16(w1f).T + b1f, 0.0).astype(np.float32)
-    h2 = np.maximum(_bf16(h1) @ _bf16(w["w2"]).T + w["b2"], 0.0).astype(np.float32)
+    h1 = np.maximum(x @ _bf16(w1f).T + _bf16_hi_lo(b1f), 0.0).astype(np.float32)
+    h2 = np.maximum(_bf16(h1) @ _bf16(w["w2"]).T + _bf16_hi_lo(w["b2"]), 0.0).astype(np.float32)
     return (h2 @ w["w3"].reshape(-1).astype(np.float32) + np.float32(w["b3"].reshape(-1)[0])).astype(np.float32)
 
 

@@ -4,13 +4,13 @@
 // (utils/preprocessing.py:12-57) + MultiHeadedMLP(48, (100, 100), (1,)) with ReLU
 // (utils/nets.py:100-132) + softmax over the legal cards of one decision.
 //
-// One CTA = one 128-row tile = 12 decisions x 10 card slots (row = [card | obs47], raw integer
-// features; the affine normalisation is folded into layer 1 when the weights are packed).
-//   layer 1: [128 x 48] x [48 x 112]   3 x tcgen05.mma (K = 16 each), A and B bf16 in shared memory,
-//            fp32 accumulator in TMEM; epilogue tcgen05.ld -> + b1 -> ReLU -> bf16 -> shared memory
-//   layer 2: [128 x 112] x [112 x 112] 7 x tcgen05.mma; epilogue + b2 -> ReLU, and
+// One tile = 128 rows = 12 decisions x 10 card slots (row = [card | obs47 | 1 1 0..], raw integer features;
+// the affine normalisation is folded into layer 1 when the weights are packed, and so are the biases).
+//   layer 1: [128 x 64] x [64 x 112]   4 x tcgen05.mma (K = 16 each), A and B bf16 in shared memory,
+//            fp32 accumulator in TMEM; epilogue tcgen05.ld -> ReLU -> bf16 -> shared memory
+//   layer 2: [128 x 112] x [112 x 112] 7 x tcgen05.mma; epilogue ReLU, and
 //   layer 3 (100 -> 1) as an fp32 dot product in the same epilogue (N = 1 is not a tensor-core shape)
-//   softmax over each decision's legal slots, probabilities out.
+//   softmax over each decision's legal slots by warp shuffles, probabilities out.
 // Hidden width 100 is padded to 112 (tcgen05 N granularity 16 at M = 128); padded weights are zero.
 // Features are built on chip from int8 observations, so the GEMMs never read activations from HBM.
 #include "policy_tile.cuh"
@@ -21,8 +21,11 @@ namespace nimmt {
 // obs: int8 [D][47]; probs: float [D][10] (0 for empty slots); logits (optional): float [D][10].
 // kProbGroups groups share one copy of the weights in shared memory and each own 128 TMEM columns, an
 // mbarrier and a named barrier, so one group's epilogue (TMEM -> registers -> bf16 -> shared memory)
-// runs under the other groups' MMAs.
+// runs under the other groups' MMAs.  Within a group, warp w carries decisions 3 w .. 3 w + 2 in lanes
+// 0..29 (lanes 30, 31 are dead rows), so the softmax is ten shuffles.
 constexpr int kProbGroups = 4;
+constexpr int kObsWords = kDecPerTile * kObs / 4;   // 141 32-bit words of observation bytes per tile
+
 __global__ void __launch_bounds__(kTileRows * kProbGroups, 1)
 k_policy_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restrict__ blob, float* __restrict__ probs, float* __restrict__ logits) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -34,55 +37,77 @@ k_policy_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
     if (threadIdx.x < kProbGroups) mbar_init(&bars[threadIdx.x], 1);
     if (threadIdx.x == 0) fence_barrier_init();
     if (threadIdx.x < 32) tmem_alloc(&tmem_slot, kTmemColsPerGroup * kProbGroups);
+    const int group = threadIdx.x / kTileRows, tid = threadIdx.x % kTileRows, bar_id = 1 + group;
+    uint8_t* gbuf = smem + kSmemGroups + group * kGroupBytes;
+    init_feature_constants(gbuf, tid);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const int group = threadIdx.x / kTileRows, tid = threadIdx.x % kTileRows, bar_id = 1 + group;
     const uint32_t tmem_base = tmem_slot + group * kTmemColsPerGroup;
-    uint8_t* gbuf = smem + kSmemGroups + group * kGroupBytes;
     uint32_t phase = 0;
     PhaseClock pc;
-    float* tile_logits = reinterpret_cast<float*>(gbuf + kGLogits);
+    uint16_t* tile_rows = reinterpret_cast<uint16_t*>(gbuf + kGRows);   // bf16 [12][48]: [d][0] unused, [d][1 + k] = obs k
     int8_t* tile_obs = reinterpret_cast<int8_t*>(gbuf + kGObs);
 
-    const int64_t num_tiles = (D + kDecPerTile - 1) / kDecPerTile;
-    for (int64_t tile = (int64_t)blockIdx.x * kProbGroups + group; tile < num_tiles; tile += (int64_t)gridDim.x * kProbGroups) {
-        const int dec_local = tid / kSlots, slot = tid % kSlots;
-        const int64_t dec = tile * kDecPerTile + dec_local;
-        const bool in_range = tid < kDecPerTile * kSlots && dec < D;
-        // stage the tile's 12 x 47 observation bytes with coalesced 4-byte loads (564 B, 4-byte aligned)
-        {
-            const int64_t first_byte = tile * (kDecPerTile * kObs), total_bytes = D * kObs;
-            for (int wd = tid; wd < kDecPerTile * kObs / 4; wd += kTileRows) {
-                const int64_t byte = first_byte + 4 * wd;
-                uint32_t v = 0;
-                if (byte + 4 <= total_bytes) v = *reinterpret_cast<const uint32_t*>(obs + byte);
-                else for (int i = 0; i < 4; ++i) if (byte + i < total_bytes) v |= (uint32_t)(uint8_t)obs[byte + i] << (8 * i);
-                reinterpret_cast<uint32_t*>(tile_obs)[wd] = v;
-            }
+    const int lane = tid & 31, warp = tid >> 5;
+    const int dloc = lane / kSlots, slot = lane % kSlots;
+    const int first = (dloc < kDecPerWarp ? dloc : kDecPerWarp - 1) * kSlots;
+    const int dec_local = warp * kDecPerWarp + (dloc < kDecPerWarp ? dloc : kDecPerWarp - 1);
+
+    // the tile's 12 x 47 observation bytes as 141 coalesced 4-byte loads (564 B, 4-byte aligned), fetched one
+    // tile ahead into registers so that the latency hides under the previous tile's GEMMs
+    const int64_t total_bytes = D * kObs;
+    auto load_word = [&](int64_t tile, int wd) -> uint32_t {
+        const int64_t byte = tile * (kDecPerTile * kObs) + 4 * wd;
+        uint32_t v = 0;
+        if (byte + 4 <= total_bytes) v = *reinterpret_cast<const uint32_t*>(obs + byte);
+        else for (int i = 0; i < 4; ++i) if (byte + i < total_bytes) v |= (uint32_t)(uint8_t)obs[byte + i] << (8 * i);
+        return v;
+    };
+    const int64_t num_tiles = (D + kDecPerTile - 1) / kDecPerTile, stride = (int64_t)gridDim.x * kProbGroups;
+    int64_t tile = (int64_t)blockIdx.x * kProbGroups + group;
+    uint32_t w0 = 0, w1 = 0;
+    if (tile < num_tiles) {
+        w0 = load_word(tile, tid);
+        if (tid < kObsWords - kTileRows) w1 = load_word(tile, kTileRows + tid);
+    }
+    for (; tile < num_tiles; tile += stride) {
+        reinterpret_cast<uint32_t*>(tile_obs)[tid] = w0;
+        if (tid < kObsWords - kTileRows) reinterpret_cast<uint32_t*>(tile_obs)[kTileRows + tid] = w1;
+        group_sync(bar_id);
+        if (tile + stride < num_tiles) {
+            w0 = load_word(tile + stride, tid);
+            if (tid < kObsWords - kTileRows) w1 = load_word(tile + stride, kTileRows + tid);
+        }
+        // int8 -> bf16 once per decision (not once per row): 72 threads convert one 8-feature chunk each
+        if (tid < kDecPerTile * kFeatChunks) {
+            const int d = tid / kFeatChunks, c = tid % kFeatChunks;
+            const int8_t* o = tile_obs + d * kObs + 8 * c - 1;
+            uint32_t p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p[i] = bf16x2_bits(c == 0 && i == 0 ? 0 : o[2 * i], o[2 * i + 1]);
+            *reinterpret_cast<uint4*>(tile_rows + d * kIn + 8 * c) = make_uint4(p[0], p[1], p[2], p[3]);
         }
         group_sync(bar_id);
-        const int8_t* o = tile_obs + dec_local * kObs;
-        const int card = in_range ? o[slot] : -1;      // hand slot: the candidate card, -1 if empty (env.py:209-210)
-        const bool live = in_range && card >= 0;
-        write_feature_row(gbuf, tid, [&](int k) -> float { return live ? (float)(k == 0 ? card : o[k - 1]) : 0.0f; });
+        const int64_t dec = tile * kDecPerTile + dec_local;
+        const bool in_range = dloc < kDecPerWarp && dec < D;
+        const int card = in_range ? tile_obs[dec_local * kObs + slot] : -1;   // hand slot: the candidate card, -1 if empty (env.py:209-210)
+#pragma unroll
+        for (int c = 0; c < kFeatChunks; ++c) {
+            uint4 v = *reinterpret_cast<const uint4*>(tile_rows + dec_local * kIn + 8 * c);
+            if (c == 0) v.x = (v.x & 0xFFFF0000u) | bf16_bits(card);
+            store_feature_chunk(gbuf, tid, c, v);
+        }
 
-        const float logit = mlp_tile(smem + kSmemBlob, gbuf, tmem_base, &bars[group], phase, tid, bar_id, pc);
+        const float logit = mlp_tile(smem + kSmemBlob, gbuf, tmem_base, &bars[group], phase, tid, bar_id, pc, [](uint32_t) {});
 
-        tile_logits[tid] = logit;
-        group_sync(bar_id);
+        const uint32_t live = (__ballot_sync(0xffffffffu, card >= 0) >> first) & 0x3FFu;
+        float e[kSlots], z, m;
+        decision_softmax(logit, first, live, e, z, m);
         if (in_range) {
-            // softmax over the decision's legal slots (agents/mcts.py:207,227: Softmax(dim=0) over the rows)
-            float m = -INFINITY;
-            for (int s = 0; s < kSlots; ++s)
-                if (o[s] >= 0) m = fmaxf(m, tile_logits[dec_local * kSlots + s]);
-            float z = 0.0f;
-            for (int s = 0; s < kSlots; ++s)
-                if (o[s] >= 0) z += __expf(tile_logits[dec_local * kSlots + s] - m);
             probs[dec * kSlots + slot] = card >= 0 ? __expf(logit - m) / z : 0.0f;
             if (logits) logits[dec * kSlots + slot] = card >= 0 ? logit : 0.0f;
         }
-        group_sync(bar_id);   // tile_logits, tile_obs and the A operands are free again
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -108,22 +133,33 @@ int nimmt_policy_pack_weights(const float* w1, const float* b1, const float* w2,
             scale[k] = 2.0 / ((double)s.hi - s.lo);                 // preprocessing.py:56-57 with out range [-1, 1]
             shift[k] = -1.0 - 2.0 * s.lo / ((double)s.hi - s.lo);
         }
-    float* b1p = reinterpret_cast<float*>(blob + kOffB1);
-    float* b2p = reinterpret_cast<float*>(blob + kOffB2);
+    auto put1 = [&](int n, int k, uint16_t v) { *reinterpret_cast<uint16_t*>(blob + kOffW1 + canon_off(n, k, kInChunks)) = v; };
+    auto put2 = [&](int n, int k, uint16_t v) { *reinterpret_cast<uint16_t*>(blob + kOffW2 + canon_off(n, k, kHidChunks)) = v; };
+    // a bias as two bf16 terms: hi = bf16(b), lo = bf16(b - hi); both meet a constant-1 input in the GEMM
+    auto split = [](float b, uint16_t& hi, uint16_t& lo) {
+        hi = float_to_bf16_rne(b);
+        lo = float_to_bf16_rne(b - bf16_to_float(hi));
+    };
     float* w3p = reinterpret_cast<float*>(blob + kOffW3);
     for (int n = 0; n < kHid; ++n) {
         double acc = b1[n];
         for (int k = 0; k < kIn; ++k) {
             const double w = w1[n * kIn + k];
             acc += w * shift[k];
-            *reinterpret_cast<uint16_t*>(blob + kOffW1 + canon_off(n, k, kInChunks)) = float_to_bf16_rne((float)(w * scale[k]));
+            put1(n, k, float_to_bf16_rne((float)(w * scale[k])));
         }
-        b1p[n] = (float)acc;
-        for (int k = 0; k < kHid; ++k)
-            *reinterpret_cast<uint16_t*>(blob + kOffW2 + canon_off(n, k, kHidChunks)) = float_to_bf16_rne(w2[n * kHid + k]);
-        b2p[n] = b2[n];
+        uint16_t hi, lo;
+        split((float)acc, hi, lo);
+        put1(n, kBiasCol, hi);
+        put1(n, kBiasCol + 1, lo);
+        for (int k = 0; k < kHid; ++k) put2(n, k, float_to_bf16_rne(w2[n * kHid + k]));
+        split(b2[n], hi, lo);
+        put2(n, kOneUnit, hi);
+        put2(n, kOneUnit + 1, lo);
         w3p[n] = w3[n];
     }
+    put1(kOneUnit, kBiasCol, 0x3F80);       // units 100, 101 of layer 1: relu(1 * 1) = 1, the inputs that carry b2
+    put1(kOneUnit + 1, kBiasCol, 0x3F80);
     *reinterpret_cast<float*>(blob + kOffB3) = b3;
     return NIMMT_OK;
 }

@@ -18,30 +18,37 @@
 #include "policy_tile.cuh"
 #include "puct.cuh"
 #include "rollout.cuh"
+#include <climits>
 
 namespace nimmt {
 
 constexpr int kModePuct = 0, kModeStratified = 2;   // mode 1: the root move is sampled from the policy like every other move
 
-// Board block of a tree in observation order (env.py:186-207), 36 bytes so that it is restored with word copies.
-struct BoardBlock {
-    int8_t board[kRows][6];            // -1 padded
-    uint8_t len[kRows], top[kRows], sum[kRows];
+// Board features of a tree as bf16 bit patterns, in the order and chunking the policy rows consume them
+// (env.py:186-207): 80 bytes, restored from the root with five 16-byte copies.
+struct alignas(16) BoardFeat {
+    uint16_t len[kRows], pad[4];       // features 12..15: second half of chunk 1
+    uint16_t top[kRows], sum[kRows];   // chunk 2
+    uint16_t board[kRows][6];          // chunks 3..5, -1 padded
 };
+static_assert(sizeof(BoardFeat) == 80, "BoardFeat is copied as five uint4");
 
 struct TreeState {
-    int8_t hand[kMaxPlayers][kHand];   // each ascending, -1 padded (the observation's hand block)
-    alignas(4) BoardBlock cur, root;
+    alignas(16) uint16_t hand[kMaxPlayers][16];   // bf16: [p][0] unused (the row's own card goes there), [p][1..10] the hand,
+                                                  // ascending and -1 padded (the observation's hand block), [p][11] = P
+    BoardFeat cur, root;
+    int8_t sorted[kMaxPlayers][kHand];            // the opponents' freshly dealt hands (integers), per rollout
     int8_t action[kMaxPlayers];
     int8_t root_hand[kHand];
     uint8_t deck[kCards];              // the agent's unseen cards (any order), then garbage
-    int n_avail, root_n, valid, outcome, first_index;
-    float root_prob[kHand], cur_prob[kHand];
+    uint8_t draw[kCards];              // this rollout's Fisher-Yates swap targets
+    int n_avail, root_n, valid;
+    float root_prob[kHand];
     RootStats stats;
 };
-static_assert(sizeof(BoardBlock) == 36, "BoardBlock is copied as nine 32-bit words");
 
 __device__ __forceinline__ float uniform01(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+constexpr uint16_t kBf16MinusOne = 0xBF80;
 
 template <int P>
 __global__ void __launch_bounds__(kTileRows, 1)
@@ -63,26 +70,30 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
         fence_barrier_init();
     }
     if (threadIdx.x < 32) tmem_alloc(&tmem_slot, kTmemColsPerGroup);
+    uint8_t* gbuf = smem + kSmemGroups;
+    init_feature_constants(gbuf, threadIdx.x);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
     uint32_t phase = 0;
     PhaseClock pc;
-    uint8_t* gbuf = smem + kSmemGroups;
 
     // thread roles: row = (decision, hand slot).  Warp w carries decisions 3 w .. 3 w + 2 in lanes 0..29, so the
     // softmax, the sampling and the hand update of a decision are warp shuffles; lanes 30 and 31 are dead rows.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int dloc = lane / kSlots, slot = lane % kSlots;
-    const int dec = warp * 3 + dloc;
-    const int gbase = (dloc < 3 ? dloc : 2) * kSlots;                        // first lane of this row's decision
-    const bool row_live = dloc < 3 && dec < T * P;
+    const int dec = warp * kDecPerWarp + dloc;
+    const int gbase = (dloc < kDecPerWarp ? dloc : kDecPerWarp - 1) * kSlots;   // first lane of this row's decision
+    const bool row_live = dloc < kDecPerWarp && dec < T * P;
     const int tree_l = row_live ? dec / P : 0, player = row_live ? dec % P : 0;
     const bool is_dec = row_live && slot == 0;                               // one thread per (tree, player)
     const bool is_tree = is_dec && player == 0;                              // one thread per tree
     const int tree_g = blockIdx.x * T + tree_l;
     TreeState& ts = trees[tree_l];
+    RowKeys rk_root, rk;                                                     // live in the tree thread's registers
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { rk_root.set_row(r, 0, 1, 0); rk.set_row(r, 0, 1, 0); }
 
     // ---- decode the root (BaseMCAgent's view, agents/mcts.py:62-89) ----
     if (is_tree) {
@@ -102,18 +113,23 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
                 for (int c = 0; c < kCards; ++c)
                     if (mask_has(pool, c)) ts.deck[na++] = (uint8_t)c;
                 ts.n_avail = na;
+#pragma unroll
                 for (int r = 0; r < kRows; ++r) {
                     int len = 0;
                     for (int i = 0; i < 6; ++i) {
                         const int c = root.rows[r][i];
                         const bool ok = c < kCards && len == i && i < 5;
-                        ts.root.board[r][i] = ok ? (int8_t)c : (int8_t)-1;
+                        ts.root.board[r][i] = ok ? (uint16_t)bf16_bits(c) : kBf16MinusOne;
                         len += ok;
                     }
-                    ts.root.len[r] = (uint8_t)lite.len(r);
-                    ts.root.top[r] = (uint8_t)lite.top(r);
-                    ts.root.sum[r] = (uint8_t)lite.sum(r);
+                    ts.root.len[r] = (uint16_t)bf16_bits(lite.len(r));
+                    ts.root.top[r] = (uint16_t)bf16_bits(lite.top(r));
+                    ts.root.sum[r] = (uint16_t)bf16_bits(lite.sum(r));
+                    ts.root.pad[r] = 0;
+                    rk_root.set_row(r, lite.top(r), lite.len(r), lite.sum(r));
                 }
+                for (int p = 0; p < P; ++p)
+                    for (int i = 0; i < 16; ++i) ts.hand[p][i] = i == 11 ? (uint16_t)bf16_bits(P) : (uint16_t)0;
                 root_stats_clear(ts.stats);
                 for (int i = 0; i < kHand; ++i) ts.root_prob[i] = 0.0f;
             }
@@ -124,25 +140,35 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
     for (int t = 0; t < T; ++t) n_root_max = max(n_root_max, trees[t].valid ? trees[t].root_n : 0);
     const bool tree_ok = row_live && ts.valid;
     const int root_n = tree_ok ? ts.root_n : 0;
+    const int n_avail = tree_ok ? ts.n_avail : 0;
+    const int need = (P - 1) * root_n;                // cards dealt to the opponents per rollout
+    uint16_t* my_hand = ts.hand[player];
 
     pc.start();
     for (int j = 0; j < n_mc; ++j) {
+        const uint64_t rollout_id = ((uint64_t)tree_g << 24) | (uint64_t)j;
         // ---- new rollout: restore the root, deal the opponents (agents/mcts.py:108-127) ----
-        if (tree_ok && player == 0) {
-            ts.hand[0][slot] = ts.root_hand[slot];
-            if (slot < 9) reinterpret_cast<uint32_t*>(&ts.cur)[slot] = reinterpret_cast<const uint32_t*>(&ts.root)[slot];
+        int card = -1;                                // the card in this row's hand slot
+        if (tree_ok) {
+            if (player == 0) {
+                card = ts.root_hand[slot];
+                my_hand[1 + slot] = (uint16_t)bf16_bits(card);
+                if (slot < 5) reinterpret_cast<uint4*>(&ts.cur)[slot] = reinterpret_cast<const uint4*>(&ts.root)[slot];
+            }
+            // partial Fisher-Yates over the unseen cards, the first (P-1) n entries become the opponents' hands:
+            // the swap targets are drawn in parallel (one per row), the swaps run on one thread below
+            const int i = player * kSlots + slot;
+            if (i < need) {
+                Philox rng(seed, rollout_id, 0x6465616cu, (uint32_t)i);
+                ts.draw[i] = (uint8_t)(i + (int)below(rng.next().x, (uint32_t)(n_avail - i)));
+            }
         }
+        int outcome = 0, first_index = -1;
+        rk = rk_root;
+        __syncthreads();
         if (is_tree && tree_ok) {
-            ts.outcome = 0;
-            ts.first_index = -1;
-            // partial Fisher-Yates over the unseen cards: the first (P-1) n entries become the opponents' hands
-            Philox rng(seed, ((uint64_t)tree_g << 24) | (uint64_t)j, 0x6465616cu, 0);
-            uint4 rw = make_uint4(0, 0, 0, 0);
-            const int need = (P - 1) * root_n, n_avail = ts.n_avail;
             for (int i = 0; i < need; ++i) {
-                if ((i & 3) == 0) rw = rng.next();
-                const uint32_t w = (i & 3) == 0 ? rw.x : (i & 3) == 1 ? rw.y : (i & 3) == 2 ? rw.z : rw.w;
-                const int k = i + (int)below(w, (uint32_t)(n_avail - i));
+                const int k = ts.draw[i];
                 const uint8_t a = ts.deck[i], b = ts.deck[k];
                 ts.deck[i] = b; ts.deck[k] = a;
             }
@@ -154,120 +180,120 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
             int rank = 0;
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) rank += __shfl_sync(kFull, v, gbase + s) < v;
+            if (opp) ts.sorted[player][slot < root_n ? rank : slot] = (int8_t)(slot < root_n ? v : -1);   // distinct cards: ranks are a permutation
+            __syncwarp();
             if (opp) {
-                if (slot < root_n) ts.hand[player][rank] = (int8_t)v;   // cards are distinct, so ranks are a permutation
-                else ts.hand[player][slot] = -1;
+                card = ts.sorted[player][slot];
+                my_hand[1 + slot] = (uint16_t)bf16_bits(card);
             }
+            __syncwarp();
         }
-        __syncthreads();
         pc.mark(10);
 
         for (int turn = 0; turn < n_root_max; ++turn) {
             const bool playing = tree_ok && turn < root_n;   // shorter roots idle until the longest finishes
             const int h = root_n - turn;                      // cards in every hand of this tree
-            // ---- features of every (tree, player, slot) row (env.py:174-212 layout behind the candidate card) ----
-            const int card = playing ? ts.hand[player][slot] : -1;
-            const bool live = playing && card >= 0;
-            write_feature_row(gbuf, threadIdx.x, [&](int k) -> float {
-                if (!live) return 0.0f;
-                if (k == 0) return (float)card;
-                if (k <= 10) return (float)ts.hand[player][k - 1];
-                if (k == 11) return (float)P;
-                if (k <= 15) return (float)ts.cur.len[k - 12];
-                if (k <= 19) return (float)ts.cur.top[k - 16];
-                if (k <= 23) return (float)ts.cur.sum[k - 20];
-                return (float)ts.cur.board[(k - 24) / 6][(k - 24) % 6];
-            });
+            // ---- features of every (tree, player, slot) row: [card | env.py:174-212 observation | 1 1 0 ..], six 16-byte chunks ----
+            {
+                uint4 c0 = *reinterpret_cast<const uint4*>(my_hand);
+                c0.x = (c0.x & 0xFFFF0000u) | bf16_bits(card);
+                const uint2 h1 = *reinterpret_cast<const uint2*>(my_hand + 8), ln = *reinterpret_cast<const uint2*>(ts.cur.len);
+                store_feature_chunk(gbuf, threadIdx.x, 0, c0);
+                store_feature_chunk(gbuf, threadIdx.x, 1, make_uint4(h1.x, h1.y, ln.x, ln.y));
+                store_feature_chunk(gbuf, threadIdx.x, 2, *reinterpret_cast<const uint4*>(ts.cur.top));
+#pragma unroll
+                for (int c = 0; c < 3; ++c) store_feature_chunk(gbuf, threadIdx.x, 3 + c, reinterpret_cast<const uint4*>(ts.cur.board)[c]);
+            }
             pc.mark(0);
-            const float logit = mlp_tile(smem + kSmemBlob, gbuf, tmem_base, &bar, phase, threadIdx.x, 0, pc);
-
-            // ---- softmax over the decision's hand, every lane of the decision redundantly (mcts.py:219-228) ----
-            float pr[kSlots];
-            float m = -INFINITY;
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                pr[s] = __shfl_sync(kFull, logit, gbase + s);
-                if (s < h) m = fmaxf(m, pr[s]);
-            }
-            float z = 0.0f;
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) {
-                pr[s] = s < h ? __expf(pr[s] - m) : 0.0f;
-                z += pr[s];
-            }
-#pragma unroll
-            for (int s = 0; s < kSlots; ++s) pr[s] /= z;
+            // Categorical(probs).sample() (mcts.py:212-213) by the Gumbel-max trick: argmax_s (logit_s - log(-log u_s)) is
+            // a draw from softmax(logits), so a sampled move needs no exponentials, no sum and no CDF.  The row's
+            // Gumbel variate is computed while the tensor core runs layer 1.
+            float gumbel = 0.0f;
+            const float logit = mlp_tile(smem + kSmemBlob, gbuf, tmem_base, &bar, phase, threadIdx.x, 0, pc, [&](uint32_t token) {
+                Philox rng(seed, rollout_id, (0x73616d70u + (uint32_t)turn) ^ token, (uint32_t)(player * 16 + slot));
+                const float u = ((float)(rng.next().x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // in (0, 1)
+                gumbel = -__logf(-__logf(u));
+                pin_result(gumbel);
+            });
 
             // ---- player 0's first move: PUCT over the earlier outcomes, or the stratified schedule ----
             int pick = -1;
             if (turn == 0) {
-                if (playing && player == 0) {
-                    const float mine = slot < h ? __expf(logit - m) / z : 0.0f;
-                    ts.cur_prob[slot] = mine;
-                    if (j == 0) ts.root_prob[slot] = mine;
-                }
-                __syncwarp();
-                if (is_tree && playing) {
-                    if (mode == kModePuct) pick = puct_choose(ts.stats, ts.cur_prob, h, c_puct, nullptr);   // mcts.py:281-293
-                    else if (mode == kModeStratified) pick = j % h;
-                }
-                __syncwarp();
-                pick = __shfl_sync(kFull, pick, gbase);
-            }
-            // ---- every other move: Categorical(probs).sample() (mcts.py:212-213) by inverse CDF ----
-            {
-                Philox rng(seed, ((uint64_t)tree_g << 24) | (uint64_t)j, 0x73616d70u + (uint32_t)turn, (uint32_t)player);
-                const float u = uniform01(rng.next().x);
-                float acc = 0.0f;
-                int below_u = 0;   // the CDF is non-decreasing: the first s with u < cdf[s] is the number of s with u >= cdf[s]
+                // softmax over the decision's hand (mcts.py:219-228), every lane of the decision redundantly
+                float e[kSlots], z, m;
+                decision_softmax(logit, gbase, playing ? (1u << h) - 1u : 0u, e, z, m);
+                const float mine = slot < h ? __expf(logit - m) / z : 0.0f;
+                if (playing && player == 0 && j == 0) ts.root_prob[slot] = mine;
+                if (mode == kModePuct) {
+                    // mcts.py:281-302: lane a computes the PUCT value of card a; the strict '>' scan over ascending cards
+                    // (NaN never wins, so 0/0 everywhere picks the first card) runs on the gathered values
+                    double mine_puct = -INFINITY;
+                    if (playing && player == 0 && slot < h) mine_puct = puct_value(ts.stats, puct_bounds(ts.stats), slot, mine, c_puct);
+                    double best = -INFINITY;
+                    int choice = 0;
 #pragma unroll
-                for (int s = 0; s < kSlots; ++s) {
-                    acc += pr[s];
-                    below_u += (s < h && !(u < acc)) ? 1 : 0;
+                    for (int s = 0; s < kSlots; ++s) {
+                        const double p = __shfl_sync(kFull, mine_puct, gbase + s);
+                        if (s < h && p > best) { best = p; choice = s; }
+                    }
+                    if (player == 0) pick = choice;
+                } else if (mode == kModeStratified) {
+                    if (playing && player == 0) pick = j % h;
                 }
-                if (pick < 0) pick = min(below_u, h - 1);
+            }
+            // ---- every other move: the largest perturbed logit among the decision's cards ----
+            {
+                // order-preserving integer image of the float, hand slot in the low four bits (ties: lowest slot)
+                const uint32_t bits = __float_as_uint(logit + gumbel);
+                const int ordered = (int)(bits ^ ((uint32_t)((int)bits >> 31) >> 1));
+                const int key = playing && slot < h ? (ordered & ~15) | (15 - slot) : INT_MIN;
+                const uint32_t members = dloc < kDecPerWarp ? 0x3FFu << gbase : 0xC0000000u;   // the ten lanes of this decision
+                const int winner = __reduce_max_sync(members, key);
+                if (pick < 0) pick = 15 - (winner & 15);
             }
             // ---- hand.remove(card): the lanes behind the pick shift down by one ----
             const int chosen = __shfl_sync(kFull, card, gbase + max(pick, 0));
             const int next = __shfl_sync(kFull, card, (lane + 1) & 31);
             if (playing) {
-                ts.hand[player][slot] = (int8_t)(slot < pick ? card : (slot < kSlots - 1 ? next : -1));
+                const int moved = slot < pick ? card : (slot < kSlots - 1 ? next : -1);
+                if (moved != card) my_hand[1 + slot] = (uint16_t)bf16_bits(moved);
+                card = moved;
                 if (slot == 0) {
                     ts.action[player] = (int8_t)chosen;
-                    if (player == 0 && turn == 0) ts.first_index = pick;
+                    if (player == 0 && turn == 0) first_index = pick;
                 }
             }
             pc.mark(7);
             __syncthreads();
             pc.mark(8);
 
-            // ---- one thread per tree: env.step (env.py:120-136) on the shared-memory board ----
+            // ---- one thread per tree: env.step (env.py:120-136); row keys in registers, features in shared memory ----
             if (is_tree && playing) {
-                RowKeys rk;
-                for (int r = 0; r < kRows; ++r) rk.set_row(r, ts.cur.top[r], ts.cur.len[r], ts.cur.sum[r]);
                 int keys[P];
 #pragma unroll
                 for (int p = 0; p < P; ++p) keys[p] = ((int)ts.action[p] << 4) | p;
                 sort_keys<P>(keys);
-                int outcome = ts.outcome;
 #pragma unroll
                 for (int i = 0; i < P; ++i) {
                     const int c = keys[i] >> 4;
                     int row;
                     uint32_t keep_len;
                     const int pen = rk.place(c, values[c], row, keep_len);
-                    if (keep_len == 0)
-                        for (int s = 1; s < 6; ++s) ts.cur.board[row][s] = -1;
-                    ts.cur.board[row][keep_len] = (int8_t)c;
+                    if (keep_len == 0) {
+#pragma unroll
+                        for (int s = 1; s < 6; ++s) ts.cur.board[row][s] = kBf16MinusOne;
+                    }
+                    ts.cur.board[row][keep_len] = (uint16_t)bf16_bits(c);
                     if ((keys[i] & 15) == 0) outcome -= pen;                                         // mcts.py:150
                 }
-                ts.outcome = outcome;
-                for (int r = 0; r < kRows; ++r) { ts.cur.len[r] = (uint8_t)rk.len(r); ts.cur.top[r] = (uint8_t)rk.top(r); ts.cur.sum[r] = (uint8_t)rk.sum(r); }
+                *reinterpret_cast<uint2*>(ts.cur.len) = make_uint2(bf16x2_bits(rk.len(0), rk.len(1)), bf16x2_bits(rk.len(2), rk.len(3)));
+                *reinterpret_cast<uint4*>(ts.cur.top) = make_uint4(bf16x2_bits(rk.top(0), rk.top(1)), bf16x2_bits(rk.top(2), rk.top(3)),
+                                                                   bf16x2_bits(rk.sum(0), rk.sum(1)), bf16x2_bits(rk.sum(2), rk.sum(3)));
             }
             __syncthreads();
             pc.mark(9);
         }
-        if (is_tree && tree_ok) root_stats_add(ts.stats, ts.first_index, ts.outcome);                // mcts.py:100
+        if (is_tree && tree_ok) root_stats_add(ts.stats, first_index, outcome);                      // mcts.py:100
     }
 
 #ifdef NIMMT_PHASE_CLOCKS

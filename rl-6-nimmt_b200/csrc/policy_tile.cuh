@@ -1,5 +1,13 @@
 // policy_tile.cuh — one 128-row tile of the Alpha0.5 policy net on tcgen05 (shared by the batched
 // leaf-evaluation kernel and the policy-rollout kernel).  See policy_kernels.cu for the overview.
+//
+// Both kernels are bound by per-thread instruction latency around the MMAs, not by the MMAs, so the tile is
+// built to keep the threads' share small:
+//   * biases ride in the GEMMs: features 48, 49 of every row are the constant 1 and carry b1 split into two
+//     bf16 terms (hi + lo, ~16 mantissa bits); layer 1's units 100, 101 are the constant 1 and carry b2 the
+//     same way.  Epilogue 1 is cvt.relu.bf16x2 + store, epilogue 2 is max + fma per column.
+//   * feature rows are assembled from bf16 data that is already laid out in 16-byte chunks (six vector
+//     loads and stores per row) instead of 48 scalar conversions.
 #pragma once
 #include <cstring>
 
@@ -10,20 +18,23 @@
 
 namespace nimmt {
 
-constexpr int kIn = 48, kHid = 100, kHidPad = 112, kObs = 47;
-constexpr int kTileRows = 128, kSlots = 10, kDecPerTile = 12;
-constexpr int kInChunks = kIn / 8, kHidChunks = kHidPad / 8;
-constexpr uint32_t kW1Bytes = (kHidPad / 8) * kInChunks * 128;    // 10752
+constexpr int kIn = 48, kInPad = 64, kHid = 100, kHidPad = 112, kObs = 47;
+constexpr int kBiasCol = 48;     // features 48, 49 = 1.0 (b1 hi, lo); 50..63 = 0
+constexpr int kOneUnit = 100;    // hidden-1 units 100, 101 = 1.0 (b2 hi, lo); 102..111 = 0
+constexpr int kTileRows = 128, kSlots = 10, kDecPerTile = 12, kDecPerWarp = 3;
+constexpr int kInChunks = kInPad / 8, kHidChunks = kHidPad / 8, kFeatChunks = kIn / 8;
+constexpr uint32_t kW1Bytes = (kHidPad / 8) * kInChunks * 128;    // 14336
 constexpr uint32_t kW2Bytes = (kHidPad / 8) * kHidChunks * 128;   // 25088
-constexpr uint32_t kOffW1 = 0, kOffW2 = kOffW1 + kW1Bytes, kOffB1 = kOffW2 + kW2Bytes, kOffB2 = kOffB1 + kHidPad * 4;
-constexpr uint32_t kOffW3 = kOffB2 + kHidPad * 4, kOffB3 = kOffW3 + kHidPad * 4, kBlobBytes = kOffB3 + 16;   // 37200
-constexpr uint32_t kA1Bytes = (kTileRows / 8) * kInChunks * 128;  // 12288
+constexpr uint32_t kOffW1 = 0, kOffW2 = kOffW1 + kW1Bytes, kOffW3 = kOffW2 + kW2Bytes, kOffB3 = kOffW3 + kHidPad * 4;
+constexpr uint32_t kBlobBytes = kOffB3 + 16;                      // 39888
+constexpr uint32_t kA1Bytes = (kTileRows / 8) * kInChunks * 128;  // 16384
 constexpr uint32_t kA2Bytes = (kTileRows / 8) * kHidChunks * 128; // 28672
 // dynamic shared memory: the weight blob, then one buffer set per tile group (a group = 128 threads that
 // push tiles through the net independently of the other groups of the CTA, sharing only the weights)
 constexpr uint32_t kSmemBlob = 0, kSmemGroups = (kBlobBytes + 127) / 128 * 128;
-constexpr uint32_t kGA1 = 0, kGA2 = kGA1 + kA1Bytes, kGLogits = kGA2 + kA2Bytes, kGObs = kGLogits + kTileRows * 4;
-constexpr uint32_t kGroupBytes = (kGObs + kDecPerTile * kObs + 4 + 127) / 128 * 128;
+constexpr uint32_t kGA1 = 0, kGA2 = kGA1 + kA1Bytes, kGRows = kGA2 + kA2Bytes;             // kGRows: bf16 [12][48] staged decisions
+constexpr uint32_t kGObs = kGRows + kDecPerTile * kIn * 2;                                  // int8 [12][47] (+ pad)
+constexpr uint32_t kGroupBytes = (kGObs + kDecPerTile * kObs + 12 + 127) / 128 * 128;       // 46848
 constexpr uint32_t kTmemColsPerGroup = 128;
 __host__ __device__ constexpr uint32_t policy_smem_bytes(int groups) { return kSmemGroups + (uint32_t)groups * kGroupBytes; }
 
@@ -41,6 +52,12 @@ static inline uint16_t float_to_bf16_rne(float f) {
     u += 0x7FFFu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
 }
+static inline float bf16_to_float(uint16_t h) {
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
 
 // max(x, 0) rounded to bf16, two at a time, in one instruction (x1 lands in the upper half).
 __device__ __forceinline__ uint32_t relu_pack_bf16x2(float x0, float x1) {
@@ -48,6 +65,9 @@ __device__ __forceinline__ uint32_t relu_pack_bf16x2(float x0, float x1) {
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x1), "f"(x0));
     return d;
 }
+// bf16 bit pattern of a small integer (|v| <= 256 is exact).
+__device__ __forceinline__ uint32_t bf16_bits(int v) { return (uint32_t)__bfloat16_as_ushort(__int2bfloat16_rn(v)); }
+__device__ __forceinline__ uint32_t bf16x2_bits(int lo, int hi) { return bf16_bits(lo) | (bf16_bits(hi) << 16); }
 
 // Bring-up instrument (-DNIMMT_PHASE_CLOCKS): thread 0 of block 0 accumulates clock64() deltas per phase
 // and prints them when the kernel ends.  Compiled out of the product build.
@@ -70,10 +90,23 @@ struct PhaseClock {
 #endif
 };
 
-// Epilogue 1 for hidden chunks [C0, C1) of 16 columns: TMEM -> + b1 -> ReLU -> bf16 -> layer 2's A operand.
+// Once per kernel: the constant chunks (features 48..63) of this thread's row of the layer-1 A operand.
+__device__ __forceinline__ void init_feature_constants(uint8_t* gbuf, int row) {
+    *reinterpret_cast<uint4*>(gbuf + kGA1 + canon_off(row, kBiasCol, kInChunks)) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // 1.0, 1.0, 0 ..
+    *reinterpret_cast<uint4*>(gbuf + kGA1 + canon_off(row, kBiasCol + 8, kInChunks)) = make_uint4(0u, 0u, 0u, 0u);
+}
+// Chunk c (features 8 c .. 8 c + 7, bf16) of one row of the layer-1 A operand.
+__device__ __forceinline__ void store_feature_chunk(uint8_t* gbuf, int row, int c, uint4 v) {
+    *reinterpret_cast<uint4*>(gbuf + kGA1 + canon_off(row, 0, kInChunks) + c * 128) = v;
+}
+
+// See mlp_tile's while_mma1: marks a value as needed at this point of the instruction stream.
+__device__ __forceinline__ void pin_result(float& x) { asm volatile("" : "+f"(x)); }
+
+// Epilogue 1 for hidden chunks [C0, C1) of 16 columns: TMEM -> ReLU -> bf16 -> layer 2's A operand.
 // The chunk's TMEM loads are all issued before the single wait, so their latencies overlap.
 template <int C0, int C1>
-__device__ __forceinline__ void epilogue1_chunks(uint32_t lane_taddr, const float* b1, uint8_t* a2_row) {
+__device__ __forceinline__ void epilogue1_chunks(uint32_t lane_taddr, uint8_t* a2_row) {
     uint32_t v[C1 - C0][16];
 #pragma unroll
     for (int c = C0; c < C1; ++c) tmem_ld16(lane_taddr + c * 16, v[c - C0]);
@@ -82,17 +115,16 @@ __device__ __forceinline__ void epilogue1_chunks(uint32_t lane_taddr, const floa
     for (int c = C0; c < C1; ++c) {
         uint32_t packed[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            packed[i] = relu_pack_bf16x2(__uint_as_float(v[c - C0][2 * i]) + b1[c * 16 + 2 * i], __uint_as_float(v[c - C0][2 * i + 1]) + b1[c * 16 + 2 * i + 1]);
+        for (int i = 0; i < 8; ++i) packed[i] = relu_pack_bf16x2(__uint_as_float(v[c - C0][2 * i]), __uint_as_float(v[c - C0][2 * i + 1]));
         uint8_t* dst = a2_row + c * 256;   // canon_off(row, 16 c, .) = canon_off(row, 0, .) + 2 chunks of 128 B per c
         *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         *reinterpret_cast<uint4*>(dst + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
     }
 }
 
-// Epilogue 2 + layer 3 for hidden chunks [C0, C1): part += w3 . relu(acc + b2), four independent chains.
+// Epilogue 2 + layer 3 for hidden chunks [C0, C1): part += w3 . relu(acc), four independent chains.
 template <int C0, int C1>
-__device__ __forceinline__ void epilogue2_chunks(uint32_t lane_taddr, const float* b2, const float* w3, float (&part)[4]) {
+__device__ __forceinline__ void epilogue2_chunks(uint32_t lane_taddr, const float* w3, float (&part)[4]) {
     uint32_t v[C1 - C0][16];
 #pragma unroll
     for (int c = C0; c < C1; ++c) tmem_ld16(lane_taddr + c * 16, v[c - C0]);
@@ -100,21 +132,20 @@ __device__ __forceinline__ void epilogue2_chunks(uint32_t lane_taddr, const floa
 #pragma unroll
     for (int c = C0; c < C1; ++c)
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            part[i & 3] = fmaf(fmaxf(__uint_as_float(v[c - C0][i]) + b2[c * 16 + i], 0.0f), w3[c * 16 + i], part[i & 3]);
+        for (int i = 0; i < 16; ++i) part[i & 3] = fmaf(fmaxf(__uint_as_float(v[c - C0][i]), 0.0f), w3[c * 16 + i], part[i & 3]);
 }
 
 // One 128-row tile through the three layers.  The 128 threads of a tile group call this together.
-//   blob: the weights; gbuf: the group's buffers, whose A1 operand the caller has filled with raw features
-//   in canonical K-major layout; tmem_base: the group's 128 accumulator columns; tid: 0..127 within the
-//   group; bar_id: the group's named barrier.  Returns this thread's row's logit.
+//   blob: the weights; gbuf: the group's buffers, whose A1 operand the caller has filled (chunks 0..5 per
+//   tile, the constant chunks once); tmem_base: the group's 128 accumulator columns; tid: 0..127 within the
+//   group; bar_id: the group's named barrier; while_mma1(token = 0): work the caller wants done while layer 1's MMAs
+//   run (the threads would only poll the mbarrier).  Returns this thread's row's logit.
+template <class F>
 __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, uint32_t tmem_base, uint64_t* bar, uint32_t& phase, int tid,
-                                          int bar_id, PhaseClock& pc) {
+                                          int bar_id, PhaseClock& pc, F while_mma1) {
     const int row = tid, warp = tid >> 5;
     const uint32_t a1 = smem_u32(gbuf + kGA1), a2 = smem_u32(gbuf + kGA2);
     const uint32_t w1 = smem_u32(blob + kOffW1), w2 = smem_u32(blob + kOffW2);
-    const float* b1 = reinterpret_cast<const float*>(blob + kOffB1);
-    const float* b2 = reinterpret_cast<const float*>(blob + kOffB2);
     const float* w3 = reinterpret_cast<const float*>(blob + kOffW3);
     const float b3 = *reinterpret_cast<const float*>(blob + kOffB3);
     constexpr uint32_t idesc = umma_idesc_bf16(kTileRows, kHidPad);
@@ -128,17 +159,24 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     if (tid == 0) {
         tc_fence_after_sync();
 #pragma unroll
-        for (int ks = 0; ks < kIn / 16; ++ks)
+        for (int ks = 0; ks < kInPad / 16; ++ks)
             umma_bf16(tmem_base, umma_desc(a1 + ks * 256, 128, kInChunks * 128), umma_desc(w1 + ks * 256, 128, kInChunks * 128), idesc, ks > 0);
         umma_commit(bar);
+    }
+    {   // caller's work, pinned between the MMA issue and the wait: its input passes through a volatile asm placed
+        // here and its results through another one (see pin_result), which keeps the compiler from sinking it to the
+        // first use after the epilogues
+        uint32_t token;
+        asm volatile("mov.u32 %0, 0;" : "=r"(token));
+        while_mma1(token);
     }
     mbar_wait_or_trap(bar, phase);
     phase ^= 1u;
     tc_fence_after_sync();
     pc.mark(2);
-    // epilogue 1: + b1, ReLU, round to bf16, store as layer 2's A operand (4 + 3 chunks bound the live registers)
-    epilogue1_chunks<0, 4>(lane_taddr, b1, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
-    epilogue1_chunks<4, kHidPad / 16>(lane_taddr, b1, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
+    // epilogue 1: ReLU, round to bf16, store as layer 2's A operand (4 + 3 chunks bound the live registers)
+    epilogue1_chunks<0, 4>(lane_taddr, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
+    epilogue1_chunks<4, kHidPad / 16>(lane_taddr, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
     // ---- layer 2 ----
     fence_async_smem();
     tc_fence_before_sync();
@@ -156,30 +194,33 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     phase ^= 1u;
     tc_fence_after_sync();
     pc.mark(5);
-    // epilogue 2 + layer 3: logit = w3 . relu(acc + b2) + b3, fp32
-    float logit = b3;
+    // epilogue 2 + layer 3: logit = w3 . relu(acc) + b3, fp32
     float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    epilogue2_chunks<0, 4>(lane_taddr, b2, w3, part);
-    epilogue2_chunks<4, kHidPad / 16>(lane_taddr, b2, w3, part);
-    logit += (part[0] + part[1]) + (part[2] + part[3]);
-    tc_fence_before_sync();      // ordered before the caller's next __syncthreads / next tile's MMA
+    epilogue2_chunks<0, 4>(lane_taddr, w3, part);
+    epilogue2_chunks<4, kHidPad / 16>(lane_taddr, w3, part);
+    const float logit = b3 + ((part[0] + part[1]) + (part[2] + part[3]));
+    tc_fence_before_sync();      // ordered before the caller's next barrier / the next tile's MMA
     pc.mark(6);
     return logit;
 }
 
-// Writes one 48-feature row as bf16 into the layer-1 A operand; feature(k) returns the raw value of
-// input k (k = 0: candidate card, k = 1..47: observation entry k - 1, env.py:174-212 layout).
-template <class F>
-__device__ __forceinline__ void write_feature_row(uint8_t* gbuf, int row, F feature) {
+// Softmax over one decision's hand slots by warp shuffles.  The decision's ten rows sit in lanes
+// first .. first + 9 of the warp; live_mask has bit s set when slot s holds a card.  Every lane of the
+// decision ends up with all ten un-normalised weights e[s] = exp(logit_s - max) (0 for empty slots) and
+// their sum z and the maximum m; probabilities are e[s] / z (agents/mcts.py:207,227: Softmax(dim=0) over the
+// rows).  Must be called by all 32 lanes.
+__device__ __forceinline__ void decision_softmax(float logit, int first, uint32_t live_mask, float (&e)[kSlots], float& z, float& m) {
+    m = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < kInChunks; ++c) {
-        uint32_t packed[4];
+    for (int s = 0; s < kSlots; ++s) {
+        e[s] = __shfl_sync(0xffffffffu, logit, first + s);
+        if ((live_mask >> s) & 1u) m = fmaxf(m, e[s]);
+    }
+    z = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(feature(c * 8 + 2 * i), feature(c * 8 + 2 * i + 1));
-            packed[i] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-        *reinterpret_cast<uint4*>(gbuf + kGA1 + canon_off(row, c * 8, kInChunks)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    for (int s = 0; s < kSlots; ++s) {
+        e[s] = (live_mask >> s) & 1u ? __expf(e[s] - m) : 0.0f;
+        z += e[s];
     }
 }
 

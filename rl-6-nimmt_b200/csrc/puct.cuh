@@ -57,25 +57,37 @@ NIMMT_HD double median_outcome(const RootStats& s) {
     return 0.0;
 }
 
+// (max, min, "mean") of _normalize_q (agents/mcts.py:304-315).
+struct PuctBounds { double mx, mn, md, root_n; };
+NIMMT_HD PuctBounds puct_bounds(const RootStats& s) {
+    PuctBounds b;
+    if (s.total < 10) {
+        b.mx = 0.0; b.mn = -10.0; b.md = -5.0;
+    } else {
+        b.mn = (double)-s.max_mag;
+        b.mx = (double)-s.min_mag;
+        b.md = median_outcome(s);   // np.median
+    }
+    b.root_n = sqrt((double)s.total + 1.0e-9);
+    return b;
+}
+
+// PUCT value of legal card a (agents/mcts.py:295-302).
+NIMMT_HD double puct_value(const RootStats& s, const PuctBounds& b, int a, float prob, float c_puct) {
+    const double q = s.count[a] > 0 ? (double)s.sum[a] / (double)s.count[a] : b.md;
+    double qn = (q - b.mn) / (b.mx - b.mn);        // 0/0 -> NaN when all outcomes are equal: kept
+    qn = qn < 0.0 ? 0.0 : (qn > 1.0 ? 1.0 : qn);   // np.clip; NaN compares false twice and passes through
+    const float cp = c_puct * prob;                // float32 product first, as numpy does (python float * float32 array)
+    return qn + (double)cp * b.root_n / (1.0 + (double)s.count[a]);
+}
+
 // Returns the index (into the n legal cards, ascending) PUCT selects; pucts[] receives the values.
 NIMMT_HD int puct_choose(const RootStats& s, const float* probs, int n, float c_puct, double* pucts) {
-    double mx, mn, md;
-    if (s.total < 10) {
-        mx = 0.0; mn = -10.0; md = -5.0;
-    } else {
-        mn = (double)-s.max_mag;
-        mx = (double)-s.min_mag;
-        md = median_outcome(s);   // np.median
-    }
-    const double root_n = sqrt((double)s.total + 1.0e-9);
+    const PuctBounds b = puct_bounds(s);
     int choice = 0;
     double best = -INFINITY;
     for (int a = 0; a < n; ++a) {
-        const double q = s.count[a] > 0 ? (double)s.sum[a] / (double)s.count[a] : md;
-        double qn = (q - mn) / (mx - mn);          // 0/0 -> NaN when all outcomes are equal: kept
-        qn = qn < 0.0 ? 0.0 : (qn > 1.0 ? 1.0 : qn);   // np.clip; NaN compares false twice and passes through
-        const float cp = c_puct * probs[a];        // float32 product first, as numpy does (python float * float32 array)
-        const double p = qn + (double)cp * root_n / (1.0 + (double)s.count[a]);
+        const double p = puct_value(s, b, a, probs[a], c_puct);
         if (pucts) pucts[a] = p;
         if (p > best) { best = p; choice = a; }
     }
