@@ -7,10 +7,13 @@ small spec objects instead of per-game Python agents:
 
     RandomSeat()                                   DrunkHamster (agents/random.py)
     MCSSeat(mc_per_card=10, mc_max=100)            MCSAgent (agents/mcts.py:180-188)
-    PolicySeat(net, mc_max=100, puct=True)         PUCTAgent / PolicyMCSAgent (agents/mcts.py:191-323), inference only
+    PolicySeat(net, mc_max=100, puct=True)         PUCTAgent / PolicyMCSAgent (agents/mcts.py:191-323)
 
 Everything — card memory, root construction, rollouts, the decision rule, the env step — runs in
-kernels; the host only sequences launches.  Learning is not part of this harness.
+kernels; the host only sequences launches.  ``PolicySeat(..., learn=True)`` closes the Alpha0.5 self-play loop
+(SURVEY.md §8f row 2): the seat's observations and chosen cards of every turn stay on the device and, when the
+games end, one batched imitation step (train.py; agents/mcts.py:230-261) updates the net and the packed weights.
+Seats that share one ``net`` object share one optimizer and take one step on all their decisions.
 """
 import math
 
@@ -19,6 +22,7 @@ import torch
 from . import _native as N
 from . import policy as PL
 from . import rollouts as R
+from . import train as T
 from .env import BatchedSechsNimmtEnv
 
 
@@ -40,11 +44,13 @@ class MCSSeat:
 
 
 class PolicySeat(MCSSeat):
-    def __init__(self, net, mc_per_card=10, mc_max=100, puct=True, c_puct=2.0):
+    def __init__(self, net, mc_per_card=10, mc_max=100, puct=True, c_puct=2.0, learn=False):
         super().__init__(mc_per_card, mc_max)
+        self.net = net
         self.weights = PL.pack_weights(net)
         self.root_rule = N.ROOT_PUCT if puct else N.ROOT_POLICY
         self.c_puct = c_puct
+        self.learn = bool(learn)
 
 
 class BatchedGameSession:
@@ -57,7 +63,15 @@ class BatchedGameSession:
         self._stats = torch.zeros((B, R.MAX_ACTIONS, 3), dtype=torch.int64, device=dev)
         self._available = {p: torch.zeros((B, 16), dtype=torch.uint8, device=dev) for p, s in enumerate(self.seats) if not isinstance(s, RandomSeat)}
         self.results = []   # one int32 [B, P] tensor of (negative) totals per play_games() call
+        self.losses = []    # one 0-d device tensor per (play_games() call, learning net): mean per-episode imitation loss
         self.games = 0
+        # learning seats grouped by net: one Adam (agents/base.py:29-33 defaults) per distinct net
+        self._learners = {}
+        for p, s in enumerate(self.seats):
+            if isinstance(s, PolicySeat) and s.learn:
+                s.net.to(dev)
+                group = self._learners.setdefault(id(s.net), {"net": s.net, "seats": [], "optimizer": torch.optim.Adam(s.net.parameters())})
+                group["seats"].append(p)
 
     def _stream(self):
         return torch.cuda.current_stream(self.env.device).cuda_stream
@@ -66,6 +80,9 @@ class BatchedGameSession:
         env, B, P = self.env, self.env.num_games, self.env.num_players
         env.reset()
         totals = torch.zeros((B, P), dtype=torch.int32, device=env.device)
+        learning = sorted(p for g in self._learners.values() for p in g["seats"])
+        seen_obs = {p: [] for p in learning}       # per turn int8 [B,47]
+        seen_slot = {p: [] for p in learning}      # per turn [B]: hand slot of the chosen card
         for turn in range(10):
             n_cards = 10 - turn
             actions = env.random_actions()                       # every seat; MC seats are overwritten below
@@ -86,8 +103,20 @@ class BatchedGameSession:
                             R.mcs_rollouts(self._roots, P, seat.per_card(n_cards), seed=seed, out=self._stats, device=env.device)
                     N.check(self.lib.nimmt_mc_choose(N.ptr(env.state), N.ptr(self._stats), N.ptr(actions), B, P, p, self._stream()),
                             "nimmt_mc_choose")
+            if learning:
+                obs = env.observe(dtype=torch.int8)
+                for p in learning:
+                    seen_obs[p].append(obs[:, p].clone())
+                    seen_slot[p].append((obs[:, p, :10] == actions[:, p].to(torch.int8).unsqueeze(1)).to(torch.uint8).argmax(dim=1))
             rewards, done = env.step(actions)
             totals += rewards.to(torch.int32)
+        for group in self._learners.values():   # PolicyMCSAgent.learn at episode end, all episodes of all the net's seats at once
+            obs = torch.cat([o for p in group["seats"] for o in seen_obs[p]])
+            slot = torch.cat([c for p in group["seats"] for c in seen_slot[p]])
+            self.losses.append(T.imitation_step(group["net"], group["optimizer"], obs, slot, episodes=B * len(group["seats"])))
+            packed = PL.pack_weights(group["net"], device=env.device)
+            for p in group["seats"]:
+                self.seats[p].weights = packed
         self.results.append(totals)
         self.games += B
         return totals

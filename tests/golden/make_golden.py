@@ -518,7 +518,54 @@ def make_policy_rollouts(n_rollouts=2500):
     return out
 
 
+def make_policy_train(n_episodes=3):
+    """Reference PolicyMCSAgent.learn / _train (agents/mcts.py:230-261, agents/base.py:29-33): one agent, n_episodes
+    four-player games; at every turn the agent's (state, legal cards) and a chosen card are recorded together with the
+    log-probability the reference stores for it (Categorical(_compute_policy).log_prob, :212-215; constant 0 for the single
+    last card, :52-53); after each episode the reference's own _train() runs (loss = -sum log_prob, Adam defaults).
+    Saved: initial weights, the decisions, the loss of every episode, the weights after every episode."""
+    import torch
+    from torch.distributions import Categorical
+    torch.manual_seed(5)
+    agent = ref.mcts.PolicyMCSAgent(mc_max=10)
+    agent.train()                                   # creates Adam with default kwargs (base.py:29-33)
+    out = {"w0_" + k.replace(".", "_"): v.detach().numpy().copy() for k, v in agent.state_dict().items()}
+    np.random.seed(31)
+    env = Env(4, verbose=False)
+    obs, legal_n, chosen, losses, ref_logp = [], [], [], [], []
+    for ep in range(n_episodes):
+        states, legal = env.reset()
+        done = False
+        while not done:
+            st = torch.tensor(states[0]).to(torch.float)
+            la = list(map(int, legal[0]))
+            idx = int(np.random.randint(len(la)))
+            if len(la) == 1:
+                lp = torch.tensor(0.0)
+            else:
+                lp = Categorical(agent._compute_policy(la, st)).log_prob(torch.tensor(idx))
+            obs.append(np.array(states[0], np.int64)); legal_n.append(len(la)); chosen.append(idx); ref_logp.append(float(lp.detach()))
+            acts = [la[idx]] + [int(np.random.choice(l)) for l in legal[1:]]
+            (states, legal), rewards, done, _ = env.step(acts)
+            agent.history.store(log_prob=lp, reward=float(rewards[0]) * agent.r_factor)
+        losses.append(agent._train())
+        agent.history.clear()
+        for k, v in agent.state_dict().items():
+            out[f"w{ep + 1}_" + k.replace(".", "_")] = v.detach().numpy().copy()
+    out["obs"] = np.array(obs, np.int8)
+    out["n_legal"] = np.array(legal_n, np.int32)
+    out["chosen"] = np.array(chosen, np.int32)
+    out["log_prob"] = np.array(ref_logp, np.float64)
+    out["loss"] = np.array(losses, np.float64)
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-policy-train":
+        pt = make_policy_train()
+        np.savez_compressed(os.path.join(HERE, "policy_train.npz"), **pt)
+        print("policy train: losses", pt["loss"], "decisions", pt["obs"].shape)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--only-policy-rollouts":
         pr = make_policy_rollouts()
         np.savez_compressed(os.path.join(HERE, "policy_rollouts.npz"), **pr)
@@ -553,6 +600,7 @@ def main():
     print("policy rows", pol["rows_in"].shape)
     pr = make_policy_rollouts()
     np.savez_compressed(os.path.join(HERE, "policy_rollouts.npz"), **pr)
+    np.savez_compressed(os.path.join(HERE, "policy_train.npz"), **make_policy_train())
 
 
 if __name__ == "__main__":

@@ -71,3 +71,50 @@ def test_alpha05_seat_runs_in_a_batch():
     totals = sess.play_games()
     assert totals.shape == (96, 3) and int(totals.max()) <= 0
     assert (sess.env.scores().int() == -totals).all()
+
+
+def test_alpha05_selfplay_loop_learns_on_device():
+    """four PUCT seats sharing one net play 64 games in lock-step, then one batched imitation step
+    (agents/mcts.py:230-261) runs on the device and the searches of the next games use the re-packed weights."""
+    from rl_6_nimmt_b200 import policy as PL
+    from rl_6_nimmt_b200 import train as T
+    torch.manual_seed(0)
+    net = PL.PolicyNet()
+    seats = [PolicySeat(net, mc_max=40, puct=True, learn=True) for _ in range(4)]
+    session = BatchedGameSession(seats, 64, seed=5)
+    before = [p.detach().clone() for p in net.parameters()]
+    blob0 = seats[0].weights.clone()
+    totals = session.play_games()
+    assert totals.shape == (64, 4) and int(totals.max()) <= 0
+    assert len(session.losses) == 1
+    loss = float(session.losses[0])
+    assert 5.0 < loss < 25.0, loss                     # nine informative turns, ~log(n) each under a fresh policy
+    assert any(not torch.equal(b, p.detach()) for b, p in zip(before, net.parameters()))
+    assert all(s.weights is seats[0].weights for s in seats) and not torch.equal(blob0, seats[0].weights)
+    session.play_games()
+    assert len(session.losses) == 2 and np.isfinite(float(session.losses[1]))
+    # the torch training path and the tcgen05 inference path are the same policy: probabilities of the chosen cards agree
+    env = session.env.reset(seed=9)
+    obs = env.observe(dtype=torch.int8)[:, 0].contiguous()
+    slot = torch.zeros(obs.shape[0], dtype=torch.int64, device=obs.device)
+    with torch.no_grad():
+        want = T.imitation_log_probs(net, obs, slot).exp()
+    got = PL.policy_probs(obs, seats[0].weights)[:, 0]
+    assert float((want - got).abs().max()) < 1e-3
+
+
+def test_imitation_reduces_the_loss_on_fixed_decisions():
+    """Repeated imitation steps on one batch of (state, chosen card) pairs drive the loss down (Adam defaults)."""
+    from rl_6_nimmt_b200 import policy as PL
+    from rl_6_nimmt_b200 import train as T
+    from rl_6_nimmt_b200.env import BatchedSechsNimmtEnv
+    torch.manual_seed(1)
+    net = PL.PolicyNet().cuda()
+    opt = torch.optim.Adam(net.parameters())
+    env = BatchedSechsNimmtEnv(2048, 4, seed=3).reset()
+    obs = env.observe(dtype=torch.int8)[:, 0].contiguous()
+    slot = torch.full((2048,), 9, dtype=torch.int64, device=obs.device)      # always the highest card
+    first = float(T.imitation_step(net, opt, obs, slot, episodes=2048))
+    for _ in range(60):
+        last = float(T.imitation_step(net, opt, obs, slot, episodes=2048))
+    assert abs(first - np.log(10)) < 0.3 and last < 0.5 * first, (first, last)
