@@ -114,6 +114,12 @@ NIMMT_API int nimmt_step(void *state, const uint8_t *actions, int8_t *rewards, u
 NIMMT_API int nimmt_observe(const void *state, void *obs, uint8_t *n_legal, int64_t num_games, int num_players,
                   int include_summaries, int dtype, void *stream);
 
+/* Packs per-game flag bytes (the `done` or `illegal` output of nimmt_step: 0 / non-zero) into bits, game b ->
+ * bit (b & 31) of bits[b >> 5]; bits has ceil(B / 32) words, unused high bits of the last word are 0.  The
+ * reference returns `done` as one Python bool per env.step (env.py:75, 246-249); for a batch whose results go back
+ * to host memory the bit form is 8x fewer PCIe bytes. */
+NIMMT_API int nimmt_pack_flags(const uint8_t *flags, uint32_t *bits, int64_t num_games, void *stream);
+
 /* Cumulative Hornochsen per player, SechsNimmtEnv._scores (env.py:32,167): uint8 [B][P]. */
 NIMMT_API int nimmt_scores(const void *state, uint8_t *scores, int64_t num_games, int num_players, void *stream);
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "nimmt_deal_from_perm": (_int, [_vp, _vp, _i64, _int, _vp]),
     "nimmt_reset_to": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp]),
     "nimmt_step": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "nimmt_pack_flags": (_int, [_vp, _vp, _i64, _vp]),
     "nimmt_observe": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
     "nimmt_scores": (_int, [_vp, _vp, _i64, _int, _vp]),
     "nimmt_random_actions": (_int, [_vp, _vp, _i64, _int, _u64, _u32, _u64, _vp]),

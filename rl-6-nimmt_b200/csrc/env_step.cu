@@ -277,6 +277,15 @@ k_random_actions(StateView s, uint8_t* __restrict__ actions, uint64_t seed, uint
     store_bytes<P>(actions, g, act);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_pack_flags — flag bytes -> bits (one ballot per 32 games), for results that travel over PCIe.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_flags(const uint8_t* __restrict__ flags, uint32_t* __restrict__ bits, int64_t B) {
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;   // B is padded to whole warps by the launch
+    const uint32_t word = __ballot_sync(0xffffffffu, g < B && flags[g] != 0);
+    if ((threadIdx.x & 31) == 0 && g < B) bits[g >> 5] = word;
+}
+
 }  // namespace nimmt
 
 using namespace nimmt;
@@ -291,6 +300,14 @@ int nimmt_step(void* state, const uint8_t* actions, int8_t* rewards, uint8_t* do
     if (B == 0) return NIMMT_OK;
     StateView s(state, B, num_players);
     NIMMT_DISPATCH_P(num_players, launch_step<P>(s, actions, rewards, done, illegal, (cudaStream_t)stream));
+    return check_launch();
+}
+
+int nimmt_pack_flags(const uint8_t* flags, uint32_t* bits, int64_t B, void* stream) {
+    if (!flags || !bits || B < 0) return NIMMT_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(bits) & 3u) return NIMMT_E_ALIGN;
+    if (B == 0) return NIMMT_OK;
+    k_pack_flags<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(flags, bits, B);
     return check_launch();
 }
 

@@ -82,7 +82,11 @@ class BatchedSechsNimmtEnv:
         B, P = self.num_games, self.num_players
         with torch.cuda.device(self.device):
             self.state = torch.zeros(max(self.lib.nimmt_state_bytes(B, P), 16), dtype=torch.uint8, device=self.device)
-            self.rewards = torch.zeros((B, P), dtype=torch.int8, device=self.device)
+            # rewards and the bit-packed done flags share one buffer so that step_host can return both in one D2H copy
+            self._words = (B + 31) // 32
+            self._out = torch.zeros(((B * P + 15) // 16 * 16 + 4 * self._words,), dtype=torch.uint8, device=self.device)
+            self.rewards = self._out[: B * P].view(torch.int8).view(B, P)
+            self._done_bits = self._out[(B * P + 15) // 16 * 16:].view(torch.int32)
             self.done = torch.zeros((B,), dtype=torch.uint8, device=self.device)
             self.illegal = torch.zeros((B,), dtype=torch.uint8, device=self.device)
             self._actions = torch.zeros((B, P), dtype=torch.uint8, device=self.device)
@@ -151,17 +155,36 @@ class BatchedSechsNimmtEnv:
             raise InvalidMoveException(f"game {bad}: a played card is not in its owner's hand")
         return self.rewards, self.done
 
-    def step_host(self, actions_host, rewards_host, done_host):
+    def host_out_buffer(self):
+        """A pinned uint8 buffer for the packed form of step_host, plus views of its two parts:
+        (buffer, rewards int8 [B,P], done_bits int32 [ceil(B/32)])."""
+        B, P = self.num_games, self.num_players
+        buf = torch.empty_like(self._out, device="cpu").pin_memory()
+        off = (B * P + 15) // 16 * 16
+        return buf, buf[: B * P].view(torch.int8).view(B, P), buf[off:].view(torch.int32)
+
+    def step_host(self, actions_host, rewards_host, done_host=None):
         """step() for callers whose buffers live in (pinned) host memory — the end-to-end path.
 
-        Enqueues, on the current stream: H2D copy of ``actions_host`` (uint8 [B,P]), the step kernel,
-        D2H copies of rewards (int8 [B,P]) and done (uint8 [B]) into the given host tensors.  Nothing
-        synchronises; the caller syncs the stream (or an event) before reading the host buffers.
+        Enqueues, on the current stream: H2D copy of ``actions_host`` (uint8 [B,P]), the step kernel, and the
+        D2H copies of the results.  Three result forms:
+          step_host(a, rewards int8 [B,P], done uint8 [B])                one flag byte per game, two copies
+          step_host(a, rewards int8 [B,P], done int32 [ceil(B/32)])       one bit per game (game b = bit b % 32 of
+                                                                          word b // 32), two copies
+          step_host(a, out)  with out from host_out_buffer()              rewards + done bits in ONE copy
+        Nothing synchronises; the caller syncs the stream (or an event) before reading the host buffers.
         """
         self._actions.copy_(actions_host, non_blocking=True)
         self.step(self._actions)
+        if done_host is None or done_host.dtype == torch.int32:
+            with torch.cuda.device(self.device):
+                N.check(self.lib.nimmt_pack_flags(N.ptr(self.done), N.ptr(self._done_bits), self.num_games, self._stream()),
+                        "nimmt_pack_flags")
+        if done_host is None:
+            rewards_host.copy_(self._out, non_blocking=True)
+            return rewards_host
         rewards_host.copy_(self.rewards, non_blocking=True)
-        done_host.copy_(self.done, non_blocking=True)
+        done_host.copy_(self._done_bits if done_host.dtype == torch.int32 else self.done, non_blocking=True)
         return rewards_host, done_host
 
     def random_actions(self, out=None, turn=None):

@@ -8,6 +8,8 @@ small spec objects instead of per-game Python agents:
     RandomSeat()                                   DrunkHamster (agents/random.py)
     MCSSeat(mc_per_card=10, mc_max=100)            MCSAgent (agents/mcts.py:180-188)
     PolicySeat(net, mc_max=100, puct=True)         PUCTAgent / PolicyMCSAgent (agents/mcts.py:191-323)
+    ReinforceSeat(net)                             BatchedReinforceAgent.forward (agents/policy.py:137-156), inference:
+                                                   the same 48-100-100-1 net, a card sampled from its softmax, no search
 
 Everything — card memory, root construction, rollouts, the decision rule, the env step — runs in
 kernels; the host only sequences launches.  ``PolicySeat(..., learn=True)`` closes the Alpha0.5 self-play loop
@@ -53,6 +55,14 @@ class PolicySeat(MCSSeat):
         self.learn = bool(learn)
 
 
+class ReinforceSeat:
+    """A model-free policy-gradient opponent at the table: one k_policy_probs launch per turn
+    and a categorical draw per game; ``greedy=True`` plays the most probable card instead."""
+
+    def __init__(self, net, greedy=False):
+        self.net, self.weights, self.greedy = net, PL.pack_weights(net), bool(greedy)
+
+
 class BatchedGameSession:
     def __init__(self, seats, num_games, device=None, seed=0):
         self.seats = list(seats)
@@ -61,7 +71,9 @@ class BatchedGameSession:
         B, dev = num_games, self.env.device
         self._roots = torch.zeros((B, R.ROOT_BYTES), dtype=torch.uint8, device=dev)
         self._stats = torch.zeros((B, R.MAX_ACTIONS, 3), dtype=torch.int64, device=dev)
-        self._available = {p: torch.zeros((B, 16), dtype=torch.uint8, device=dev) for p, s in enumerate(self.seats) if not isinstance(s, RandomSeat)}
+        self._available = {p: torch.zeros((B, 16), dtype=torch.uint8, device=dev) for p, s in enumerate(self.seats) if isinstance(s, MCSSeat)}
+        self._generator = torch.Generator(device=dev)
+        self._generator.manual_seed(self.seed)
         self.results = []   # one int32 [B, P] tensor of (negative) totals per play_games() call
         self.losses = []    # one 0-d device tensor per (play_games() call, learning net): mean per-episode imitation loss
         self.games = 0
@@ -86,8 +98,17 @@ class BatchedGameSession:
         for turn in range(10):
             n_cards = 10 - turn
             actions = env.random_actions()                       # every seat; MC seats are overwritten below
+            obs8 = None
             for p, seat in enumerate(self.seats):
                 if isinstance(seat, RandomSeat):
+                    continue
+                if isinstance(seat, ReinforceSeat):
+                    if obs8 is None:
+                        obs8 = env.observe(dtype=torch.int8)
+                    mine = obs8[:, p].contiguous()
+                    probs = PL.policy_probs(mine, seat.weights)                    # [B,10] by hand slot, 0 for empty slots
+                    slot = probs.argmax(dim=1, keepdim=True) if seat.greedy else torch.multinomial(probs, 1, generator=self._generator)
+                    actions[:, p] = mine[:, :10].gather(1, slot).squeeze(1).to(torch.uint8)
                     continue
                 with torch.cuda.device(env.device):
                     N.check(self.lib.nimmt_mc_roots(N.ptr(env.state), N.ptr(self._available[p]), N.ptr(self._roots), B, P, p,

@@ -227,3 +227,38 @@ def test_full_size_properties_1m_games():
     dealt_val = torch.where(dealt >= 0, vals[dealt.clamp(min=0)], torch.zeros_like(dealt, dtype=torch.int32)).sum(dim=1)
     assert torch.equal(dealt_val, scores.sum(dim=1) + on_board)
     assert bool(((obs[:, 0, 11:15] >= 1) & (obs[:, 0, 11:15] <= 5)).all())
+
+
+def test_step_host_matches_step_with_byte_and_bit_done():
+    """The end-to-end path (pinned host buffers, bench.py's `e2e`): same rewards and done as step(), with done
+    delivered either as one byte or as one bit per game (nimmt_pack_flags), incl. a ragged batch size."""
+    for B in (4096, 1000):
+        P = 3
+        a_env = BatchedSechsNimmtEnv(B, P, seed=21).reset()
+        b_env = BatchedSechsNimmtEnv(B, P, seed=21).reset()
+        h_act = torch.empty((B, P), dtype=torch.uint8).pin_memory()
+        h_rew = torch.empty((B, P), dtype=torch.int8).pin_memory()
+        h_done = torch.empty((B,), dtype=torch.uint8).pin_memory()
+        h_bits = torch.empty(((B + 31) // 32,), dtype=torch.int32).pin_memory()
+        for t in range(10):
+            acts = a_env.random_actions().clone()
+            rew, done = a_env.step(acts)
+            h_act.copy_(acts)
+            torch.cuda.synchronize()
+            if t % 3 == 0:
+                b_env.step_host(h_act, h_rew, h_done)
+                torch.cuda.synchronize()
+                got_done = h_done.numpy()
+            elif t % 3 == 1:
+                out, o_rew, o_bits = b_env.host_out_buffer()
+                b_env.step_host(h_act, out)
+                torch.cuda.synchronize()
+                h_rew.copy_(o_rew)
+                got_done = np.unpackbits(o_bits.numpy().view(np.uint8), bitorder="little")[:B]
+            else:
+                b_env.step_host(h_act, h_rew, h_bits)
+                torch.cuda.synchronize()
+                got_done = np.unpackbits(h_bits.numpy().view(np.uint8), bitorder="little")[:B]
+                assert not np.unpackbits(h_bits.numpy().view(np.uint8), bitorder="little")[B:].any()
+            assert (h_rew.numpy() == rew.cpu().numpy()).all() and (got_done == done.cpu().numpy()).all(), (B, t)
+        assert got_done.all() and torch.equal(a_env.state, b_env.state)

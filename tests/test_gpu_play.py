@@ -7,7 +7,7 @@ import rl_6_nimmt_b200  # noqa: F401
 from rl_6_nimmt_b200 import _native as N
 from rl_6_nimmt_b200 import rollouts as R
 from rl_6_nimmt_b200.agents import MCSAgent
-from rl_6_nimmt_b200.play import BatchedGameSession, MCSSeat, PolicySeat, RandomSeat
+from rl_6_nimmt_b200.play import BatchedGameSession, MCSSeat, PolicySeat, RandomSeat, ReinforceSeat
 from rl_6_nimmt_b200 import policy as PL
 
 pytestmark = pytest.mark.gpu
@@ -118,3 +118,30 @@ def test_imitation_reduces_the_loss_on_fixed_decisions():
     for _ in range(60):
         last = float(T.imitation_step(net, opt, obs, slot, episodes=2048))
     assert abs(first - np.log(10)) < 0.3 and last < 0.5 * first, (first, last)
+
+
+def test_reinforce_seat_samples_from_the_policy():
+    """a BatchedReinforceAgent-style seat (agents/policy.py:137-156) plays from the net's softmax.
+    All games are forced to one root, so the empirical frequency of the first cards must match k_policy_probs."""
+    from rl_6_nimmt_b200 import policy as PL
+    torch.manual_seed(3)
+    net = PL.PolicyNet()
+    with torch.no_grad():
+        net.head_nets[0][0].weight *= 60.0              # a policy that is far from uniform
+    B = 20000
+    sess = BatchedGameSession([ReinforceSeat(net), RandomSeat(), RandomSeat()], B, seed=2)
+    env = sess.env.reset(seed=5)
+    obs0 = env.observe(dtype=torch.int8)
+    board = obs0[0, 0, -24:].reshape(4, 6).cpu().numpy()
+    hands = obs0[0, :, :10].cpu().numpy()
+    env.reset_to(np.repeat(board[None], B, 0), np.repeat(hands[None], B, 0))
+    obs = env.observe(dtype=torch.int8)[:, 0].contiguous()
+    probs = PL.policy_probs(obs, sess.seats[0].weights)[0].cpu().numpy()
+    assert probs.max() - probs.min() > 0.03             # the test has power (noise: 5 sigma = 0.018)
+    slot = torch.multinomial(PL.policy_probs(obs, sess.seats[0].weights), 1, generator=sess._generator).squeeze(1)
+    freq = np.bincount(slot.cpu().numpy(), minlength=10) / B
+    assert np.abs(freq - probs).max() < 5 * np.sqrt(0.25 / B)
+    totals = sess.play_games()                          # a full session runs and every card played was legal
+    assert totals.shape == (B, 3) and int(env.illegal.sum()) == 0
+    greedy = BatchedGameSession([ReinforceSeat(net, greedy=True), RandomSeat()], 256, seed=1).play_games()
+    assert greedy.shape == (256, 2)
