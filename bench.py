@@ -441,7 +441,7 @@ def run_ours(args):
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "players": P, "games_per_gpu_per_step": B,
-                   "l2": f"{NSETS} independent batches visited round-robin ({NSETS} x {(16 * P + 24 + 2 * P + 2) * B / 1e6:.0f} MB > 126 MB L2), no explicit flush",
+                   "l2": f"{NSETS} independent batches visited round-robin ({NSETS} x {(12 * P + 24 + 2 * P + 2) * B / 1e6:.0f} MB > 126 MB L2), no explicit flush",
                    "step": "k_step over recorded uniformly random legal actions resident in HBM, + k_deal every 10th visit of a batch; 40-step cycles replayed as a CUDA graph", "seed": 1234},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "traffic": traffic, "kernel": "k_step_smem<4>", "kernel_ms": kstep_ms,

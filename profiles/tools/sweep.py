@@ -40,7 +40,7 @@ def graph_time(fn, reps=3):
 
 
 def run(P, B):
-    state_bytes = (16 * P + 24) * B
+    state_bytes = (12 * P + 24) * B
     nsets = max(1, min(4, -(-3 * 126_000_000 // state_bytes)))
     envs = [BatchedSechsNimmtEnv(B, P, seed=11 + s, game0=s * B) for s in range(nsets)]
     tapes = [torch.empty((10, B, P), dtype=torch.uint8, device="cuda") for _ in range(nsets)]
@@ -85,15 +85,15 @@ def run(P, B):
     if B * P * 47 * 4 <= 24e9:
         obs32 = torch.empty((B, P, 47), dtype=torch.float32, device="cuda")
         out["k_observe_f32_ms"] = graph_time(lambda: [e.observe(out=obs32) for e in envs]) / nsets
-        out["observe_f32_GBs"] = (16 * P + 24 + 188 * P) * B / (out["k_observe_f32_ms"] * 1e-3) / 1e9
+        out["observe_f32_GBs"] = (12 * P + 24 + 188 * P) * B / (out["k_observe_f32_ms"] * 1e-3) / 1e9
         del obs32
     alg = 36 * P + 49
     out["env_steps_per_sec_step_only"] = B / (ms_step * 1e-3)
     out["env_steps_per_sec_with_redeal"] = B / ((ms_step + ms_deal / 10) * 1e-3)
     out["step_algorithmic_GBs"] = alg * B / (ms_step * 1e-3) / 1e9
     out["step_frac_of_measured_hbm_peak"] = out["step_algorithmic_GBs"] / PEAK
-    out["deal_GBs"] = (16 * P + 24) * B / (ms_deal * 1e-3) / 1e9
-    out["observe_i8_GBs"] = (16 * P + 24 + 47 * P) * B / (ms_obs8 * 1e-3) / 1e9
+    out["deal_GBs"] = (12 * P + 24) * B / (ms_deal * 1e-3) / 1e9
+    out["observe_i8_GBs"] = (12 * P + 24 + 47 * P) * B / (ms_obs8 * 1e-3) / 1e9
     del envs, tapes, obs8
     torch.cuda.empty_cache()
     return out
@@ -105,6 +105,6 @@ if __name__ == "__main__":
     args = ap.parse_args()
     for P in (10, 4, 2):
         for lg in (20, 22, 24, 26, 28):
-            if lg > args.max_log2 or (16 * P + 24 + 20 * P) * (1 << lg) * min(4, max(1, 400_000_000 // ((16 * P + 24) << lg) + 1)) > 120e9:
+            if lg > args.max_log2 or (12 * P + 24 + 20 * P) * (1 << lg) * min(4, max(1, 400_000_000 // ((12 * P + 24) << lg) + 1)) > 120e9:
                 continue
             print(json.dumps(run(P, 1 << lg)), flush=True)

@@ -10,41 +10,59 @@ namespace nimmt {
 
 constexpr int kStepThreads = 128;
 
+// Stored form in, stored form out (coalesced: a warp's 32 games are contiguous in every plane).
 template <int P>
-__device__ __forceinline__ void load_game(const StateView& s, int64_t g, Game<P>& gm) {
+__device__ __forceinline__ void load_hands(const StateView& s, int64_t g, HandRec (&hand)[P]) {
 #pragma unroll
-    for (int p = 0; p < P; ++p) gm.hand[p] = s.hand[(int64_t)p * s.B + g];
+    for (int p = 0; p < P; ++p) {
+        hand[p].lo = *s.cards_ptr(g, p);
+        hand[p].meta = *s.meta_ptr(g, p);
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void load_game(const StateView& s, int64_t g, GameRec<P>& gm) {
+    load_hands<P>(s, g, gm.hand);
     load_rows(s, g, gm.board);
+}
+
+// After a step: the dealt cards are immutable, only the meta words and the row record go back.
+template <int P>
+__device__ __forceinline__ void store_step(const StateView& s, int64_t g, const GameRec<P>& gm) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) *s.meta_ptr(g, p) = gm.hand[p].meta;
+    store_rows(s, g, gm.board);
+}
+
+// After a deal / reset_to: everything.
+template <int P>
+__device__ __forceinline__ void store_game(const StateView& s, int64_t g, const GameRec<P>& gm) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) *s.cards_ptr(g, p) = gm.hand[p].lo;
+    store_step<P>(s, g, gm);
 }
 
 // The planes of one game exactly as stored: lets a kernel issue all its loads first and unpack later.
 template <int P>
 struct RawGame {
-    uint4 hand[P];
+    HandRec hand[P];
     uint2 rows[3];
 };
 
 template <int P>
 __device__ __forceinline__ void load_raw(const StateView& s, int64_t g, RawGame<P>& raw) {
+    load_hands<P>(s, g, raw.hand);
+    const uint2* r = s.rows_ptr(g);
 #pragma unroll
-    for (int p = 0; p < P; ++p) raw.hand[p] = s.hand[(int64_t)p * s.B + g];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) raw.rows[k] = s.rows[3 * g + k];
+    for (int k = 0; k < 3; ++k) raw.rows[k] = r[k];
 }
 
 template <int P>
-__device__ __forceinline__ void unpack_raw(const RawGame<P>& raw, Game<P>& gm) {
+__device__ __forceinline__ void unpack_raw(const RawGame<P>& raw, GameRec<P>& gm) {
 #pragma unroll
     for (int p = 0; p < P; ++p) gm.hand[p] = raw.hand[p];
     gm.board.unpack((uint64_t)raw.rows[0].x | ((uint64_t)raw.rows[0].y << 32), (uint64_t)raw.rows[1].x | ((uint64_t)raw.rows[1].y << 32),
                     (uint64_t)raw.rows[2].x | ((uint64_t)raw.rows[2].y << 32));
-}
-
-template <int P>
-__device__ __forceinline__ void store_game(const StateView& s, int64_t g, const Game<P>& gm) {
-#pragma unroll
-    for (int p = 0; p < P; ++p) s.hand[(int64_t)p * s.B + g] = gm.hand[p];
-    store_rows(s, g, gm.board);
 }
 
 // P consecutive bytes at base + g * P, using the widest access the alignment of g * P guarantees

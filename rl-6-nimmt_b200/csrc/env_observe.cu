@@ -29,7 +29,7 @@ k_observe(StateView s, T* __restrict__ obs, uint8_t* __restrict__ n_legal) {
     const int64_t g = g0 + threadIdx.x;
     const int nb = (int)min((int64_t)TPB, s.B - g0);  // games in this block
     if (g < s.B) {
-        Game<P> gm;
+        GameRec<P> gm;
         load_game<P>(s, g, gm);
         int8_t* rec = stage + threadIdx.x * REC;
         // shared part: P, (len, top, sum per row)?, board 4x6 (env.py:188-204)
@@ -55,22 +55,15 @@ k_observe(StateView s, T* __restrict__ obs, uint8_t* __restrict__ n_legal) {
         int nl[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            // own hand ascending, -1 padded at the end (env.py:209-210)
+            // own hand ascending, -1 padded at the end (env.py:209-210): the unplayed slots, in slot order
             int8_t* h = rec + p * L;
             int cnt = 0;
-            const uint32_t words[4] = {gm.hand[p].x, gm.hand[p].y, gm.hand[p].z, gm.hand[p].w & kHighCardMask};
 #pragma unroll
-            for (int wi = 0; wi < 4; ++wi) {
-                uint32_t w = words[wi];
-                while (w) {
-                    const int b = __ffs(w) - 1;
-                    if (cnt < kHand) h[cnt] = (int8_t)(wi * 32 + b);
-                    ++cnt;
-                    w &= w - 1;
-                }
+            for (int i = 0; i < kHand; ++i) {
+                if (!((gm.hand[p].meta >> i) & 1u)) h[cnt++] = (int8_t)rec_card(gm.hand[p], i);
             }
-            nl[p] = min(cnt, kHand);
-            for (int i = nl[p]; i < kHand; ++i) h[i] = -1;
+            nl[p] = cnt;
+            for (int i = cnt; i < kHand; ++i) h[i] = -1;
 #pragma unroll
             for (int k = 0; k < L - 10; ++k) h[10 + k] = common[k];
         }

@@ -7,7 +7,7 @@ namespace nimmt {
 thread_local char g_last_error[256] = "";
 
 // ------------------------------------------------------------------------------------------
-// k_deal — SechsNimmtEnv.reset/_deal (env.py:43-51, 99-112).  Write-only: (16 P + 24) B/game.
+// k_deal — SechsNimmtEnv.reset/_deal (env.py:43-51, 99-112).  Write-only: (12 P + 24) B/game.
 // ------------------------------------------------------------------------------------------
 template <int P>
 __global__ void __launch_bounds__(kStepThreads) k_deal(StateView s, uint64_t seed, uint64_t game0) {
@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(kStepThreads) k_deal(StateView s, uint64_t see
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= s.B) return;
-    Game<P> gm;
+    GameRec<P> gm;
     deal_game<P>(gm, seed, game0 + (uint64_t)g, values, decks + threadIdx.x * kDeckStride);
     store_game<P>(s, g, gm);
 }
@@ -31,13 +31,13 @@ __global__ void __launch_bounds__(kStepThreads) k_deal_from_perm(StateView s, co
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= s.B) return;
     const uint8_t* deck = perm + g * kCards;
-    Game<P> gm;
+    GameRec<P> gm;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        uint4 h = make_uint4(0, 0, 0, 0);
+        int cards[kHand];
 #pragma unroll
-        for (int i = 0; i < kHand; ++i) mask_set(h, deck[p * kHand + i]);
-        gm.hand[p] = h;
+        for (int i = 0; i < kHand; ++i) cards[i] = deck[p * kHand + i];
+        set_dealt_hand<P>(gm, p, cards);
     }
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
@@ -58,7 +58,7 @@ k_reset_to(StateView s, const int8_t* __restrict__ board, const int8_t* __restri
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= s.B) return;
-    Game<P> gm;
+    GameRec<P> gm;
     uint4 seen = make_uint4(0, 0, 0, 0);
     bool bad = false;
     const int8_t* bsrc = board + g * (kRows * 6);
@@ -100,7 +100,7 @@ k_reset_to(StateView s, const int8_t* __restrict__ board, const int8_t* __restri
                 if (ok) { mask_set(seen, (uint32_t)c); mask_set(h, (uint32_t)c); }
             }
         }
-        gm.hand[p] = h;
+        gm.hand[p] = rec_from_mask(h);   // slots in ascending card order whatever order the caller listed them in
     }
     store_game<P>(s, g, gm);
     if (invalid) invalid[g] = bad;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kStepThreads) k_scores(StateView s, uint8_t* _
     if (g >= s.B) return;
     int sc[P];
 #pragma unroll
-    for (int p = 0; p < P; ++p) sc[p] = (int)(s.hand[(int64_t)p * s.B + g].w >> kScoreShift);
+    for (int p = 0; p < P; ++p) sc[p] = (int)((*s.meta_ptr(g, p) >> kRecScoreShift) & 0xFFu);
     store_bytes<P>(scores, g, sc);
 }
 
@@ -125,13 +125,13 @@ using namespace nimmt;
 
 extern "C" {
 
-int nimmt_abi_version(void) { return 1; }
+int nimmt_abi_version(void) { return 2; }
 
 const char* nimmt_last_cuda_error(void) { return g_last_error; }
 
 size_t nimmt_state_bytes(int64_t num_games, int num_players) {
     if (num_games < 0 || num_players < 1 || num_players > kMaxPlayers) return 0;
-    return (size_t)num_games * (size_t)(16 * num_players + 24);
+    return (size_t)StateView::bytes(num_games, num_players);   // whole tiles of 32 games, (12 P + 24) bytes per game
 }
 
 int nimmt_obs_len(int include_summaries) { return include_summaries ? 47 : 35; }

@@ -1,6 +1,5 @@
 // env_step.cu — batched env.step, random actions, and the two fused (SechsNimmtEnv.step, env.py:64-77;
-// DrunkHamster.forward, agents/random.py:8-10).  One thread per game; HBM-bandwidth bound:
-// every thread issues its P + 2 plane loads up front, works in registers, writes the planes back.
+// DrunkHamster.forward, agents/random.py:8-10).  One thread per game; HBM-bandwidth bound.
 #include "abi_common.cuh"
 #include "tma.cuh"
 
@@ -8,7 +7,7 @@ namespace nimmt {
 
 // ------------------------------------------------------------------------------------------
 // k_step — SechsNimmtEnv.step (env.py:64-77) without the observation rebuild.
-// Reads (16 P + 24) + P bytes and writes (16 P + 24) + P + 1 (+1) bytes per game.
+// Reads (12 P + 24) + P bytes and writes (4 P + 24) + P + 1 (+1) bytes per game: the dealt cards are immutable.
 // kRandom: the actions are drawn in-kernel (DrunkHamster, agents/random.py:8-10) instead of read.
 // ------------------------------------------------------------------------------------------
 template <int P, bool kRandom>
@@ -30,7 +29,7 @@ k_step(StateView s, const uint8_t* __restrict__ actions_in, uint8_t* __restrict_
     stage_card_values(values);
     __syncthreads();
     if (!valid) return;
-    Game<P> gm;
+    GameRec<P> gm;
     unpack_raw<P>(raw, gm);
     if constexpr (kRandom) {
         random_actions_game<P>(gm, seed, game0 + (uint64_t)g, turn, act);
@@ -39,7 +38,7 @@ k_step(StateView s, const uint8_t* __restrict__ actions_in, uint8_t* __restrict_
 
     int penalty[P];
     const bool legal = step_game<P>(gm, act, values, penalty);
-    if (legal) store_game<P>(s, g, gm);
+    if (legal) store_step<P>(s, g, gm);
 
     int rew[P];
 #pragma unroll
@@ -55,25 +54,26 @@ k_step(StateView s, const uint8_t* __restrict__ actions_in, uint8_t* __restrict_
 //
 // Each WARP runs its own double-buffered pipeline over tiles of 32 games, with no block-level
 // synchronisation at all:
-//     lane 0:  bulk-load tile i+1's planes (P hand planes of 512 B, 768 B of row records, 32 P
-//              action bytes — each contiguous in HBM) into the other buffer        [mbarrier]
-//     lanes:   step tile i IN PLACE in shared memory — clear one bit of each hand word, write one
-//              card byte of the row record, bump a score byte; the only per-row state kept in
-//              registers is the two comparison keys of game.cuh::RowKeys
-//     lane 0:  bulk-store the tile's planes plus rewards / done / illegal          [bulk group]
-// Working in place is what makes the kernel cheap: the plain k_step spends most of its ALU-pipe
-// slots selecting among register-resident rows and packing / unpacking them; here a placement is
-// one byte store at a computed shared-memory address.
+//     lane 0:  bulk-load tile i+1 — the tile's immutable block (dealt cards, 256 P bytes), its mutable
+//              block (slot bits + scores + row records, 128 P + 768 bytes) and 32 P action bytes, three
+//              contiguous runs of HBM — into the other buffer                      [mbarrier]
+//     lanes:   step tile i IN PLACE in shared memory — find the played card's slot among the ten dealt
+//              cards, set one bit of the player's meta word, write one card byte of the row record,
+//              add a take to the score field; the only per-row state kept in registers is the two
+//              comparison keys of game.cuh::RowKeys
+//     lane 0:  bulk-store the mutable block plus rewards / done / illegal          [bulk group]
+// The dealt cards never travel back: a step writes 4 bytes per player instead of the 16 of a card set.
 // ------------------------------------------------------------------------------------------
-constexpr int kTileGames = 32;
 constexpr int kSmemWarps = 4;   // warps per block; each is independent
 
 template <int P>
 struct TileLayout {
-    static constexpr int kHandPlane = kTileGames * 16;
-    static constexpr int kRows = P * kHandPlane;                 // 24-byte records
+    static constexpr int kCardsBytes = P * kTileGames * 8;                    // uint2 [P][32]
+    static constexpr int kMeta = kCardsBytes;                                 // uint32 [P][32]
+    static constexpr int kRows = kMeta + P * kTileGames * 4;                  // 24-byte records
+    static constexpr int kMutBytes = P * kTileGames * 4 + kTileGames * 24;
     static constexpr int kActions = kRows + kTileGames * 24;
-    static constexpr int kLoadBytes = kActions + kTileGames * P; // everything above is loaded
+    static constexpr int kLoadBytes = kActions + kTileGames * P;              // everything above is loaded
     static constexpr int kRewards = kLoadBytes;
     static constexpr int kDone = kRewards + kTileGames * P;
     static constexpr int kIllegal = kDone + kTileGames;
@@ -85,12 +85,10 @@ struct TileLayout {
 template <int P>
 __device__ __forceinline__ void issue_tile_loads(const StateView& s, const uint8_t* actions, int64_t tile, uint8_t* buf, uint64_t* bar) {
     using L = TileLayout<P>;
-    const int64_t g0 = tile * kTileGames;
     mbar_arrive_expect_tx(bar, L::kLoadBytes);
-#pragma unroll
-    for (int p = 0; p < P; ++p) bulk_load(buf + p * L::kHandPlane, s.hand + (int64_t)p * s.B + g0, L::kHandPlane, bar);
-    bulk_load(buf + L::kRows, s.rows + 3 * g0, kTileGames * 24, bar);
-    bulk_load(buf + L::kActions, actions + g0 * P, kTileGames * P, bar);
+    bulk_load(buf, reinterpret_cast<const uint8_t*>(s.cards) + tile * L::kCardsBytes, L::kCardsBytes, bar);
+    bulk_load(buf + L::kMeta, s.mut + tile * L::kMutBytes, L::kMutBytes, bar);
+    bulk_load(buf + L::kActions, actions + tile * (kTileGames * P), kTileGames * P, bar);
 }
 
 template <int P>
@@ -98,9 +96,7 @@ __device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* re
                                                   const uint8_t* buf) {
     using L = TileLayout<P>;
     const int64_t g0 = tile * kTileGames;
-#pragma unroll
-    for (int p = 0; p < P; ++p) bulk_store(s.hand + (int64_t)p * s.B + g0, buf + p * L::kHandPlane, L::kHandPlane);
-    bulk_store(s.rows + 3 * g0, buf + L::kRows, kTileGames * 24);
+    bulk_store(s.mut + tile * L::kMutBytes, buf + L::kMeta, L::kMutBytes);
     bulk_store(rewards + g0 * P, buf + L::kRewards, kTileGames * P);
     bulk_store(done + g0, buf + L::kDone, kTileGames);
     if (illegal) bulk_store(illegal + g0, buf + L::kIllegal, kTileGames);
@@ -111,24 +107,23 @@ __device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* re
 template <int P>
 __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8_t* values) {
     using L = TileLayout<P>;
-    uint8_t* hand0 = buf + lane * 16;          // + p * kHandPlane
+    const uint2* cards0 = reinterpret_cast<const uint2*>(buf) + lane;             // + p * kTileGames
+    uint32_t* meta0 = reinterpret_cast<uint32_t*>(buf + L::kMeta) + lane;         // + p * kTileGames
     uint8_t* rec = buf + L::kRows + lane * 24;
 
     int act[P];
     load_bytes<P>(buf + L::kActions, lane, act);
 
     // env.py:68-69 — check every card before touching anything
-    uint32_t word[P], bit[P];
-    int amax = 0;
+    uint32_t meta[P];
     bool legal = true;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        word[p] = *reinterpret_cast<const uint32_t*>(hand0 + p * L::kHandPlane + ((act[p] >> 3) & 12));
-        bit[p] = 1u << (act[p] & 31);
-        legal = legal && (word[p] & bit[p]) != 0u;
-        amax = imax(amax, act[p]);
+        HandRec h;
+        h.lo = cards0[p * kTileGames];
+        h.meta = meta0[p * kTileGames];
+        legal = rec_take(h, (uint32_t)act[p], meta[p]) && legal;
     }
-    legal = legal && amax < kCards;
 
     // rewards default to 0 (env.py:122); a take overwrites its player's byte below
     uint8_t* rw = buf + L::kRewards + lane * P;
@@ -143,20 +138,17 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
         for (int p = 0; p < P; ++p) rw[p] = 0;
     }
 
+    bool done = (meta0[0] & kSlotBits) == kSlotBits;   // an illegal step leaves the game as it was
     if (legal) {
-#pragma unroll
-        for (int p = 0; p < P; ++p)   // env.py:131
-            *reinterpret_cast<uint32_t*>(hand0 + p * L::kHandPlane + ((act[p] >> 3) & 12)) = word[p] & ~bit[p];
-
         // comparison keys of the four rows (game.cuh::RowKeys) from the record
         RowKeys rk;
         const uint32_t metas = *reinterpret_cast<const uint32_t*>(rec + 20);
 #pragma unroll
         for (int r = 0; r < kRows; ++r) {
-            const uint32_t meta = (metas >> (8 * r)) & 0xFFu;
-            const uint32_t top = rec[4 * ((meta & 7u) - 1u) + r];
-            rk.w[r] = (int)((top << 10) | (meta << 2) | (uint32_t)r);
-            rk.u[r] = (int)(((meta >> 3) << 2) | (uint32_t)r);
+            const uint32_t m = (metas >> (8 * r)) & 0xFFu;
+            const uint32_t top = rec[4 * ((m & 7u) - 1u) + r];
+            rk.w[r] = (int)((top << 10) | (m << 2) | (uint32_t)r);
+            rk.u[r] = (int)(((m >> 3) << 2) | (uint32_t)r);
         }
 
         int keys[P];
@@ -172,23 +164,22 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
             const int pen = rk.place(card, values[card], row, keep_len);   // env.py:126-134
             rec[4 * keep_len + row] = (uint8_t)card;   // the one byte of the record a placement changes
             if (pen != 0) {                            // a take (rare): env.py:167-169
-                uint8_t* score = hand0 + player * L::kHandPlane + 15;
-                *score = (uint8_t)(*score + pen);
+#pragma unroll
+                for (int p = 0; p < P; ++p) meta[p] += p == player ? (uint32_t)pen << kRecScoreShift : 0u;
                 rw[player] = (uint8_t)(0 - pen);
             }
         }
+#pragma unroll
+        for (int p = 0; p < P; ++p) meta0[p * kTileGames] = meta[p];   // env.py:131: the played slots are empty now
 
         uint32_t new_metas = 0;
 #pragma unroll
         for (int r = 0; r < kRows; ++r) new_metas |= (((uint32_t)rk.w[r] >> 2) & 0xFFu) << (8 * r);
         *reinterpret_cast<uint32_t*>(rec + 20) = new_metas;
+        done = (meta[0] & kSlotBits) == kSlotBits;     // env.py:246-249
     }
-    // outputs
-    {
-        const uint4 h0 = *reinterpret_cast<const uint4*>(hand0);
-        buf[L::kDone + lane] = (h0.x | h0.y | h0.z | (h0.w & kHighCardMask)) == 0u;   // env.py:246-249
-        buf[L::kIllegal + lane] = !legal;
-    }
+    buf[L::kDone + lane] = done;
+    buf[L::kIllegal + lane] = !legal;
 }
 
 template <int P>
@@ -269,9 +260,8 @@ __global__ void __launch_bounds__(kStepThreads)
 k_random_actions(StateView s, uint8_t* __restrict__ actions, uint64_t seed, uint32_t turn, uint64_t game0) {
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= s.B) return;
-    Game<P> gm;
-#pragma unroll
-    for (int p = 0; p < P; ++p) gm.hand[p] = s.hand[(int64_t)p * s.B + g];
+    GameRec<P> gm;
+    load_hands<P>(s, g, gm.hand);
     int act[P];
     random_actions_game<P>(gm, seed, game0 + (uint64_t)g, turn, act);
     store_bytes<P>(actions, g, act);

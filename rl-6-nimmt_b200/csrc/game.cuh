@@ -343,29 +343,52 @@ NIMMT_HD void sort_keys(int (&k)[N]) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// Packed-state addressing (SoA planes, include/nimmt_b200.h).
+// Packed-state addressing (include/nimmt_b200.h).  Games are stored in tiles of 32; a tile has an
+// immutable block (the dealt cards) in one array and a mutable block (slot bits + scores, row records) in another,
+// each contiguous, so that the step kernel moves a tile with one bulk copy per block:
+//     cards: [tile][P][32] uint2                       256 P bytes per tile, written by deal / reset_to only
+//     mut:   [tile]{ uint32 meta[P][32]; uint8 rows[32][24] }   128 P + 768 bytes per tile
+// A warp of 32 consecutive games reads contiguous 256- and 128-byte runs per player.
 // ----------------------------------------------------------------------------------------------
+constexpr int kTileGames = 32;
+
 struct StateView {
-    uint4* hand;   // [P][B]  128-bit hand words, one plane per player
-    uint2* rows;   // [B][3]  24-byte row records
+    uint2* cards;
+    uint8_t* mut;
     int64_t B;
-    __host__ __device__ StateView(void* base, int64_t num_games, int num_players) : B(num_games) {
-        hand = reinterpret_cast<uint4*>(base);
-        rows = reinterpret_cast<uint2*>(hand + (int64_t)num_players * num_games);
+    int P;
+    __host__ __device__ StateView(void* base, int64_t num_games, int num_players) : B(num_games), P(num_players) {
+        const int64_t tiles = (num_games + kTileGames - 1) / kTileGames;
+        cards = reinterpret_cast<uint2*>(base);
+        mut = reinterpret_cast<uint8_t*>(base) + tiles * cards_tile_bytes(num_players);
+    }
+    static __host__ __device__ constexpr int64_t cards_tile_bytes(int P) { return (int64_t)P * kTileGames * 8; }
+    static __host__ __device__ constexpr int64_t mut_tile_bytes(int P) { return (int64_t)P * kTileGames * 4 + kTileGames * 24; }
+    static __host__ __device__ constexpr int64_t bytes(int64_t B, int P) {
+        return (B + kTileGames - 1) / kTileGames * (cards_tile_bytes(P) + mut_tile_bytes(P));
+    }
+    __host__ __device__ uint2* cards_ptr(int64_t g, int p) const { return cards + ((g >> 5) * P + p) * kTileGames + (g & 31); }
+    __host__ __device__ uint32_t* meta_ptr(int64_t g, int p) const {
+        return reinterpret_cast<uint32_t*>(mut + (g >> 5) * mut_tile_bytes(P)) + p * kTileGames + (g & 31);
+    }
+    __host__ __device__ uint2* rows_ptr(int64_t g) const {   // three uint2 = the 24-byte row record
+        return reinterpret_cast<uint2*>(mut + (g >> 5) * mut_tile_bytes(P) + (int64_t)P * kTileGames * 4) + 3 * (g & 31);
     }
 };
 
 NIMMT_HD void load_rows(const StateView& s, int64_t g, Board& b) {
-    const uint2 a = s.rows[3 * g], c = s.rows[3 * g + 1], d = s.rows[3 * g + 2];
+    const uint2* r = s.rows_ptr(g);
+    const uint2 a = r[0], c = r[1], d = r[2];
     b.unpack((uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)c.x | ((uint64_t)c.y << 32), (uint64_t)d.x | ((uint64_t)d.y << 32));
 }
 
 NIMMT_HD void store_rows(const StateView& s, int64_t g, const Board& b) {
     uint64_t q0, q1, q2;
     b.pack(q0, q1, q2);
-    s.rows[3 * g] = make_uint2((uint32_t)q0, (uint32_t)(q0 >> 32));
-    s.rows[3 * g + 1] = make_uint2((uint32_t)q1, (uint32_t)(q1 >> 32));
-    s.rows[3 * g + 2] = make_uint2((uint32_t)q2, (uint32_t)(q2 >> 32));
+    uint2* r = s.rows_ptr(g);
+    r[0] = make_uint2((uint32_t)q0, (uint32_t)(q0 >> 32));
+    r[1] = make_uint2((uint32_t)q1, (uint32_t)(q1 >> 32));
+    r[2] = make_uint2((uint32_t)q2, (uint32_t)(q2 >> 32));
 }
 
 }  // namespace nimmt

@@ -16,7 +16,10 @@ __global__ void __launch_bounds__(kStepThreads)
 k_mc_roots(StateView s, uint4* __restrict__ available, nimmt_root* __restrict__ roots, int seat, int initialize) {
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= s.B) return;
-    const uint4 hand = s.hand[(int64_t)seat * s.B + g];
+    HandRec rec;
+    rec.lo = *s.cards_ptr(g, seat);
+    rec.meta = *s.meta_ptr(g, seat);
+    const uint4 hand = rec_to_mask(rec);
     uint4 av = initialize ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, kHighCardMask) : available[g];
     av.x &= ~hand.x; av.y &= ~hand.y; av.z &= ~hand.z; av.w &= ~hand.w & kHighCardMask;
     Board b;
@@ -50,8 +53,10 @@ __global__ void __launch_bounds__(kStepThreads)
 k_mc_choose(StateView s, const long long* __restrict__ stats, uint8_t* __restrict__ actions, int seat) {
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     if (g >= s.B) return;
-    const uint4 hand = s.hand[(int64_t)seat * s.B + g];
-    const int n = mask_count(hand);
+    HandRec rec;
+    rec.lo = *s.cards_ptr(g, seat);
+    rec.meta = *s.meta_ptr(g, seat);
+    const int n = rec_count(rec);
     int best = 0;
     if (n > 1) {
         double best_mean = -INFINITY;
@@ -61,7 +66,7 @@ k_mc_choose(StateView s, const long long* __restrict__ stats, uint8_t* __restric
             if (mean > best_mean) { best_mean = mean; best = a; }
         }
     }
-    actions[g * P + seat] = n > 0 ? (uint8_t)mask_select(hand, (uint32_t)best) : (uint8_t)255;
+    actions[g * P + seat] = n > 0 ? (uint8_t)rec_select(rec, (uint32_t)best) : (uint8_t)255;
 }
 
 }  // namespace nimmt

@@ -4,13 +4,20 @@
 // these, store.  Reference semantics per function are cited inline (paths relative to the
 // reference repository).
 #pragma once
-#include "game.cuh"
+#include "handrec.cuh"
 
 namespace nimmt {
 
 template <int P>
 struct Game {
     uint4 hand[P];  // bits 0..103 cards, bits 120..127 cumulative score
+    Board board;
+};
+
+// The same game in its stored form (handrec.cuh): what the kernels load, step and store.
+template <int P>
+struct GameRec {
+    HandRec hand[P];
     Board board;
 };
 
@@ -25,6 +32,27 @@ template <> struct PenaltyPack<2> { using type = uint32_t; };
 template <> struct PenaltyPack<3> { using type = uint32_t; };
 template <> struct PenaltyPack<4> { using type = uint32_t; };
 template <> struct PenaltyPack<5> { using type = uint32_t; };
+
+// SechsNimmtEnv._play_cards (env.py:120-136) on a board: the cards are resolved in ascending order, penalty[p]
+// receives the bull heads player p takes this step (reward = -penalty, env.py:169).
+template <int P>
+NIMMT_HD void play_cards(Board& board, const int (&act)[P], const uint8_t* values, int (&penalty)[P]) {
+    // sorted((card, player)) ascending by card (env.py:124-125)
+    int keys[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) keys[p] = (act[p] << 4) | p;
+    sort_keys<P>(keys);
+
+    typename PenaltyPack<P>::type packed = 0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int card = keys[i] >> 4, player = keys[i] & 15;
+        const int pen = board.place(card, values[card]);  // env.py:126-134
+        packed += (typename PenaltyPack<P>::type)pen << (6 * player);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) penalty[p] = (int)((packed >> (6 * p)) & 63u);
+}
 
 // SechsNimmtEnv.step minus the observation rebuild (env.py:64-77).
 //   act[p]      card played by player p
@@ -44,26 +72,29 @@ NIMMT_HD bool step_game(Game<P>& g, const int (&act)[P], const uint8_t* values, 
         penalty[p] = 0;
     }
     if (!legal) return false;
-
-    // sorted((card, player)) ascending by card (env.py:124-125)
-    int keys[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) keys[p] = (act[p] << 4) | p;
-    sort_keys<P>(keys);
-
-    typename PenaltyPack<P>::type packed = 0;
-#pragma unroll
-    for (int i = 0; i < P; ++i) {
-        const int card = keys[i] >> 4, player = keys[i] & 15;
-        const int pen = g.board.place(card, values[card]);  // env.py:126-134
-        packed += (typename PenaltyPack<P>::type)pen << (6 * player);
-    }
+    play_cards<P>(g.board, act, values, penalty);
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        penalty[p] = (int)((packed >> (6 * p)) & 63u);
         hand[p].w += (uint32_t)penalty[p] << kScoreShift;     // env.py:167
         g.hand[p] = hand[p];
     }
+    return true;
+}
+
+// The same step on the stored form: a played card sets its slot's bit, a take adds to the score field.
+template <int P>
+NIMMT_HD bool step_game(GameRec<P>& g, const int (&act)[P], const uint8_t* values, int (&penalty)[P]) {
+    uint32_t meta[P];
+    bool legal = true;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        legal = rec_take(g.hand[p], (uint32_t)act[p], meta[p]) && legal;
+        penalty[p] = 0;
+    }
+    if (!legal) return false;
+    play_cards<P>(g.board, act, values, penalty);
+#pragma unroll
+    for (int p = 0; p < P; ++p) g.hand[p].meta = meta[p] + ((uint32_t)penalty[p] << kRecScoreShift);   // env.py:167
     return true;
 }
 
@@ -73,6 +104,9 @@ NIMMT_HD bool game_done(const Game<P>& g) {
     return (g.hand[0].x | g.hand[0].y | g.hand[0].z | (g.hand[0].w & kHighCardMask)) == 0u;
 }
 
+template <int P>
+NIMMT_HD bool game_done(const GameRec<P>& g) { return rec_empty(g.hand[0]); }
+
 // SechsNimmtEnv._deal (env.py:99-112) with a counter RNG: a partial Fisher-Yates shuffle of the
 // 104-card deck, 10 P + 4 draws.  Draw i < 10 P goes to hand i / 10 (the reference's
 // perm[10p .. 10p+9]), draw 10 P + r opens row r (the reference's perm[103 - r]): a prefix plus
@@ -81,8 +115,25 @@ NIMMT_HD bool game_done(const Game<P>& g) {
 // kDeckStride bytes apart so that equal indices of different threads fall in different banks).
 constexpr int kDeckStride = 116;  // 29 words: odd word stride
 
+// The ten cards dealt to player p (any order) become its hand.
 template <int P>
-NIMMT_HD void deal_game(Game<P>& g, uint64_t seed, uint64_t game_id, const uint8_t* values, uint8_t* deck) {
+NIMMT_HD void set_dealt_hand(Game<P>& g, int p, int (&cards)[kHand]) {
+    uint4 h = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < kHand; ++i) mask_set(h, (uint32_t)cards[i]);
+    g.hand[p] = h;
+}
+template <int P>
+NIMMT_HD void set_dealt_hand(GameRec<P>& g, int p, int (&cards)[kHand]) {
+    sort_keys<kHand>(cards);   // the reference sorts each hand (env.py:105); slots are in ascending card order
+    uint32_t c[kHand];
+#pragma unroll
+    for (int i = 0; i < kHand; ++i) c[i] = (uint32_t)cards[i];
+    g.hand[p] = rec_from_sorted(c, kHand, 0u);
+}
+
+template <int P, class G>
+NIMMT_HD void deal_game(G& g, uint64_t seed, uint64_t game_id, const uint8_t* values, uint8_t* deck) {
     Philox rng(seed, game_id, /*stream=*/0x6e696d74u, 0);
 #pragma unroll
     for (int i = 0; i < kCards / 4; ++i) reinterpret_cast<uint32_t*>(deck)[i] = 0x03020100u + 0x04040404u * (uint32_t)i;
@@ -97,10 +148,10 @@ NIMMT_HD void deal_game(Game<P>& g, uint64_t seed, uint64_t game_id, const uint8
     };
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        uint4 h = make_uint4(0, 0, 0, 0);
+        int cards[kHand];
 #pragma unroll
-        for (int i = 0; i < kHand; ++i) mask_set(h, draw(p * kHand + i));
-        g.hand[p] = h;
+        for (int i = 0; i < kHand; ++i) cards[i] = (int)draw(p * kHand + i);
+        set_dealt_hand<P>(g, p, cards);
     }
 #pragma unroll
     for (int row = 0; row < kRows; ++row) {
@@ -111,16 +162,21 @@ NIMMT_HD void deal_game(Game<P>& g, uint64_t seed, uint64_t game_id, const uint8
 
 // DrunkHamster.forward (agents/random.py:8-10): a uniform card of each non-empty hand.
 // Random words come from the stream (seed, game_id, turn); player p uses word p.
-template <int P>
-NIMMT_HD void random_actions_game(const Game<P>& g, uint64_t seed, uint64_t game_id, uint32_t turn, int (&act)[P]) {
+NIMMT_HD int hand_count(const uint4& h) { return mask_count(h); }
+NIMMT_HD int hand_count(const HandRec& h) { return rec_count(h); }
+NIMMT_HD uint32_t hand_select(const uint4& h, uint32_t k) { return mask_select(h, k); }
+NIMMT_HD uint32_t hand_select(const HandRec& h, uint32_t k) { return rec_select(h, k); }
+
+template <int P, class G>
+NIMMT_HD void random_actions_game(const G& g, uint64_t seed, uint64_t game_id, uint32_t turn, int (&act)[P]) {
     Philox rng(seed, game_id, /*stream=*/0x61637400u + turn, 0);
     uint4 r = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         if ((p & 3) == 0) r = rng.next<7>();
         const uint32_t word = (p & 3) == 0 ? r.x : (p & 3) == 1 ? r.y : (p & 3) == 2 ? r.z : r.w;
-        const uint32_t n = (uint32_t)mask_count(g.hand[p]);
-        act[p] = n ? (int)mask_select(g.hand[p], below(word, n)) : 255;
+        const uint32_t n = (uint32_t)hand_count(g.hand[p]);
+        act[p] = n ? (int)hand_select(g.hand[p], below(word, n)) : 255;
     }
 }
 

@@ -15,7 +15,7 @@ def lib():
     if _lib is None:
         src = os.path.join(_HERE, "host_sim.cu")
         csrc = os.path.join(_HERE, "..", "..", "rl-6-nimmt_b200", "csrc")
-        newest = max(os.path.getmtime(p) for p in [src] + [os.path.join(csrc, f) for f in ("game.cuh", "step.cuh", "rollout.cuh", "puct.cuh")])
+        newest = max(os.path.getmtime(p) for p in [src] + [os.path.join(csrc, f) for f in ("game.cuh", "handrec.cuh", "step.cuh", "rollout.cuh", "puct.cuh")])
         if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
             subprocess.check_call(["nvcc", "-O1", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
                                    "-Wno-deprecated-gpu-targets", "-o", _LIB, src])
@@ -23,6 +23,11 @@ def lib():
         _lib.sim_select.restype = ctypes.c_uint
         _lib.sim_select.argtypes = [ctypes.c_uint32] * 5
     return _lib
+
+
+def set_form(form):
+    """0: the per-game logic on 104-bit card sets (Game<P>); 1: on the stored hand records (GameRec<P>, handrec.cuh)."""
+    lib().sim_set_form(int(form))
 
 
 def _p(a):

@@ -30,6 +30,29 @@ static void unpack_to_arrays(const Game<P>& g, int8_t* hands /*[P][10]*/, int8_t
     }
 }
 
+// The stored form (GameRec, handrec.cuh) goes through the same checks: converted to card sets for reading,
+// built from card sets for initialisation.
+template <int P>
+static void unpack_to_arrays(const GameRec<P>& r, int8_t* hands, int8_t* board, int16_t* scores) {
+    Game<P> g;
+    for (int p = 0; p < P; ++p) g.hand[p] = rec_to_mask(r.hand[p]);
+    g.board = r.board;
+    unpack_to_arrays<P>(g, hands, board, scores);
+}
+
+template <int P>
+static void init_game(Game<P>& g, const int8_t* rows0 /*[4][6]*/, const int8_t* hands0 /*[P][10]*/);
+
+template <int P>
+static void init_game(GameRec<P>& r, const int8_t* rows0, const int8_t* hands0) {
+    Game<P> g;
+    init_game<P>(g, rows0, hands0);
+    for (int p = 0; p < P; ++p) r.hand[p] = rec_from_mask(g.hand[p]);
+    r.board = g.board;
+}
+
+static int g_form = 0;   // 0: card sets (Game<P>), 1: stored form (GameRec<P>)
+
 template <int P>
 static void init_game(Game<P>& g, const int8_t* rows0 /*[4][6]*/, const int8_t* hands0 /*[P][10]*/) {
     for (int r = 0; r < kRows; ++r) {
@@ -49,11 +72,11 @@ static void init_game(Game<P>& g, const int8_t* rows0 /*[4][6]*/, const int8_t* 
     }
 }
 
-template <int P>
+template <int P, class G>
 static void replay(int n, int turns, const int8_t* rows0, const int8_t* hands0, const int8_t* actions, int8_t* rewards,
                    uint8_t* done, uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores) {
     for (int gi = 0; gi < n; ++gi) {
-        Game<P> g;
+        G g;
         init_game<P>(g, rows0 + gi * 24, hands0 + gi * P * 10);
         for (int t = 0; t < turns; ++t) {
             const size_t gt = (size_t)gi * turns + t;
@@ -68,21 +91,21 @@ static void replay(int n, int turns, const int8_t* rows0, const int8_t* hands0, 
     }
 }
 
-template <int P>
+template <int P, class G>
 static void deal(int n, uint64_t seed, uint64_t game0, int8_t* hands, int8_t* boards) {
     int16_t sc[P];
     for (int gi = 0; gi < n; ++gi) {
-        Game<P> g;
+        G g;
         alignas(4) uint8_t deck[kDeckStride];
         deal_game<P>(g, seed, game0 + gi, h_card_value, deck);
         unpack_to_arrays<P>(g, hands + (size_t)gi * P * 10, boards + (size_t)gi * 24, sc);
     }
 }
 
-template <int P>
+template <int P, class G>
 static void rand_act(int n, const int8_t* rows0, const int8_t* hands0, uint64_t seed, uint64_t game0, uint32_t turn, uint8_t* actions) {
     for (int gi = 0; gi < n; ++gi) {
-        Game<P> g;
+        G g;
         init_game<P>(g, rows0 + gi * 24, hands0 + gi * P * 10);
         int act[P];
         random_actions_game<P>(g, seed, game0 + gi, turn, act);
@@ -148,18 +171,22 @@ int sim_mcs(int P_, const nimmt_root* root, int64_t R, uint64_t seed, int rank, 
 }
 int sim_replay(int P_, int n, int turns, const int8_t* rows0, const int8_t* hands0, const int8_t* actions, int8_t* rewards,
                uint8_t* done, uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores) {
-    DISPATCH(P_, replay<P>(n, turns, rows0, hands0, actions, rewards, done, illegal, hands, boards, scores));
+    if (g_form) { DISPATCH(P_, (replay<P, GameRec<P>>(n, turns, rows0, hands0, actions, rewards, done, illegal, hands, boards, scores))); }
+    else { DISPATCH(P_, (replay<P, Game<P>>(n, turns, rows0, hands0, actions, rewards, done, illegal, hands, boards, scores))); }
     return 0;
 }
 int sim_deal(int P_, int n, uint64_t seed, uint64_t game0, int8_t* hands, int8_t* boards) {
-    DISPATCH(P_, deal<P>(n, seed, game0, hands, boards));
+    if (g_form) { DISPATCH(P_, (deal<P, GameRec<P>>(n, seed, game0, hands, boards))); }
+    else { DISPATCH(P_, (deal<P, Game<P>>(n, seed, game0, hands, boards))); }
     return 0;
 }
 int sim_random_actions(int P_, int n, const int8_t* rows0, const int8_t* hands0, uint64_t seed, uint64_t game0, uint32_t turn,
                        uint8_t* actions) {
-    DISPATCH(P_, rand_act<P>(n, rows0, hands0, seed, game0, turn, actions));
+    if (g_form) { DISPATCH(P_, (rand_act<P, GameRec<P>>(n, rows0, hands0, seed, game0, turn, actions))); }
+    else { DISPATCH(P_, (rand_act<P, Game<P>>(n, rows0, hands0, seed, game0, turn, actions))); }
     return 0;
 }
+void sim_set_form(int form) { g_form = form; }
 int sim_check_sort_networks() {
     int bad = 0;
     bad |= check_network<2>(); bad |= check_network<3>(); bad |= check_network<4>(); bad |= check_network<5>();

@@ -33,8 +33,9 @@ def test_header_symbols_exported_and_bound():
 def test_host_only_entry_points():
     lib = N.lib()
     assert lib.nimmt_abi_version() == N.ABI_VERSION
-    assert lib.nimmt_state_bytes(1 << 20, 4) == (16 * 4 + 24) << 20
-    assert lib.nimmt_state_bytes(10, 10) == 1840
+    assert lib.nimmt_state_bytes(1 << 20, 4) == (12 * 4 + 24) << 20       # (12 P + 24) bytes per game, whole tiles of 32
+    assert lib.nimmt_state_bytes(33, 2) == 2 * 32 * (12 * 2 + 24)
+    assert lib.nimmt_state_bytes(10, 10) == 32 * (12 * 10 + 24)
     assert lib.nimmt_state_bytes(1, 0) == 0 and lib.nimmt_state_bytes(1, 11) == 0 and lib.nimmt_state_bytes(-1, 4) == 0
     assert lib.nimmt_obs_len(1) == 47 and lib.nimmt_obs_len(0) == 35
     vals = [lib.nimmt_card_value(c) for c in range(104)]

@@ -8,7 +8,27 @@ import pytest
 
 import oracle
 from conftest import GOLDEN
-from host_sim import deal, lib, random_actions, replay
+from host_sim import deal, lib, random_actions, replay, set_form
+
+
+@pytest.fixture(autouse=True, params=[0, 1], ids=["card-sets", "stored-records"])
+def form(request):
+    """Every test runs on both forms of the per-game logic: 104-bit card sets (Game<P>) and the stored hand records
+    the kernels step in place (GameRec<P>, handrec.cuh)."""
+    set_form(request.param)
+    yield request.param
+    set_form(0)
+
+
+def test_both_forms_deal_and_choose_identically():
+    for P in (2, 4, 10):
+        set_form(0)
+        h0, b0 = deal(P, 500, seed=11)
+        a0 = random_actions(P, b0, h0, seed=4, turn=3)
+        set_form(1)
+        h1, b1 = deal(P, 500, seed=11)
+        a1 = random_actions(P, b1, h1, seed=4, turn=3)
+        assert (h0 == h1).all() and (b0 == b1).all() and (a0 == a1).all()
 
 
 def test_sorting_networks_zero_one_principle():
