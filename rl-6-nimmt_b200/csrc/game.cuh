@@ -100,6 +100,46 @@ struct Philox {
 // n <= 104): far below any test in this repo can resolve; stated in DESIGN.md §6.
 NIMMT_HD uint32_t below(uint32_t r, uint32_t n) { return umulhi32(r, n); }
 
+// Two uniform integers from one 32-bit word: the high half of r * n is the draw, the low half — the position of r
+// within its bucket, spread over the full 32-bit range on a lattice of spacing n — serves as the random word of a second
+// draw.  Joint bias <= n1 * n2 / 2^32 (< 2.6e-6 for n <= 104).  `r` is replaced by the low half.
+NIMMT_HD uint32_t below_keep(uint32_t& r, uint32_t n) {
+    const uint64_t prod = (uint64_t)r * n;
+    r = (uint32_t)prod;
+    return (uint32_t)(prod >> 32);
+}
+
+// The random words of one turn of a P-player game: two draws per word, so ceil(P / 2) words per turn, taken from one
+// Philox4x32-7 call per floor(4 / words) turns (P = 4: one call per two turns; P >= 9 needs two calls per turn).
+template <int P>
+struct TurnWords {
+    static constexpr int kWords = (P + 1) / 2;
+    static constexpr int kTurnsPerCall = kWords <= 4 ? 4 / kWords : 1;
+    uint4 r;
+    uint32_t w[kWords];
+    NIMMT_HD TurnWords() : r(make_uint4(0, 0, 0, 0)) {}
+    template <class Rng>
+    NIMMT_HD void begin_turn(Rng& rng, int turn) {
+        const int phase = turn % kTurnsPerCall;
+        if (phase == 0) r = rng.template next<7>();
+        const uint32_t c[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < kWords && i < 4; ++i) {
+            uint32_t v = c[i];                                 // phase 0
+#pragma unroll
+            for (int ph = 1; ph < kTurnsPerCall; ++ph) v = phase == ph ? c[(ph * kWords + i) & 3] : v;
+            w[i] = v;
+        }
+        if constexpr (kWords > 4) w[4] = rng.template next<7>().x;
+    }
+    // draw number i of the turn (compile-time i), uniform in [0, n)
+    template <int I>
+    NIMMT_HD uint32_t draw(uint32_t n) {
+        if constexpr ((I & 1) == 0) return below_keep(w[I >> 1], n);
+        else return below(w[I >> 1], n);
+    }
+};
+
 // ----------------------------------------------------------------------------------------------
 // 104-bit card sets in a uint4 (x = cards 0..31, y = 32..63, z = 64..95, w bits 0..7 = 96..103).
 // ----------------------------------------------------------------------------------------------

@@ -78,6 +78,20 @@ NIMMT_HD bool make_rollout_root(const nimmt_root& root, const uint8_t* values, R
     return true;
 }
 
+// The opponents' cards of one turn: player p draws the next card of the shrinking pool (compile-time recursion so that
+// every draw knows which half of which random word it consumes).
+template <int P, int I>
+NIMMT_HD void draw_opponents(TurnWords<P>& words, uint8_t* deck, uint32_t& drawn, uint32_t n_pool, int (&keys)[P]) {
+    if constexpr (I < P) {
+        const uint32_t j = drawn + words.template draw<I>(n_pool - drawn);
+        const uint32_t card = deck[j];
+        deck[j] = deck[drawn];   // position `drawn` is never read again: half a swap suffices
+        ++drawn;
+        keys[I] = (int)(card << 4) | I;
+        draw_opponents<P, I + 1>(words, deck, drawn, n_pool, keys);
+    }
+}
+
 // Plays one rollout.  `first_index` = rank (ascending) of the card forced as player 0's first move
 // (stratified root: the caller runs the same number of rollouts for every legal card).  `deck` is 116
 // bytes of scratch private to the caller.  Cards are drawn by partial Fisher-Yates: the opponents'
@@ -94,34 +108,21 @@ NIMMT_HD int rollout(const RolloutRoot& rr, int first_index, const uint8_t* valu
     uint32_t drawn = 0;
     const uint32_t n_pool = (uint32_t)rr.n_pool;
     int outcome = 0;
-    uint4 r = make_uint4(0, 0, 0, 0);
-    int used = 4;
-    auto next_word = [&]() -> uint32_t {
-        if (used == 4) { r = rng.next<7>(); used = 0; }
-        const uint32_t w = used == 0 ? r.x : used == 1 ? r.y : used == 2 ? r.z : r.w;
-        ++used;
-        return w;
-    };
-    bool first_turn = true;
+    TurnWords<P> words;
+    int turn = 0;
     while (n_own > 0) {
         int keys[P];
+        words.begin_turn(rng, turn);
         // player 0: forced card on the first turn, uniform afterwards (mcts.py:140-145, 187-188)
         {
-            const uint32_t w = next_word();
-            const uint32_t idx = first_turn ? (uint32_t)first_index : below(w, (uint32_t)n_own);
+            const uint32_t pick = words.template draw<0>((uint32_t)n_own);
+            const uint32_t idx = turn == 0 ? (uint32_t)first_index : pick;
             const int card = deck[kOwnOffset + idx];
             --n_own;
             deck[kOwnOffset + idx] = deck[kOwnOffset + n_own];   // swap-remove
             keys[0] = card << 4;
         }
-#pragma unroll
-        for (int p = 1; p < P; ++p) {
-            const uint32_t j = drawn + below(next_word(), n_pool - drawn);
-            const uint32_t card = deck[j];
-            deck[j] = deck[drawn];   // position `drawn` is never read again: half a swap suffices
-            ++drawn;
-            keys[p] = (int)(card << 4) | p;
-        }
+        draw_opponents<P, 1>(words, deck, drawn, n_pool, keys);
         sort_keys<P>(keys);
 #pragma unroll
         for (int i = 0; i < P; ++i) {
@@ -131,7 +132,7 @@ NIMMT_HD int rollout(const RolloutRoot& rr, int first_index, const uint8_t* valu
             const int pen = board.place(card, values[card], row, keep_len);
             outcome -= (keys[i] & 15) == 0 ? pen : 0;   // mcts.py:150: player 0's rewards only
         }
-        first_turn = false;
+        ++turn;
     }
     return outcome;
 }

@@ -137,11 +137,19 @@ NIMMT_HD void deal_game(G& g, uint64_t seed, uint64_t game_id, const uint8_t* va
     Philox rng(seed, game_id, /*stream=*/0x6e696d74u, 0);
 #pragma unroll
     for (int i = 0; i < kCards / 4; ++i) reinterpret_cast<uint32_t*>(deck)[i] = 0x03020100u + 0x04040404u * (uint32_t)i;
+    // two draws per 32-bit word (below_keep): one Philox4x32-7 call serves eight cards
     uint4 r = make_uint4(0, 0, 0, 0);
+    uint32_t spare = 0;
     auto draw = [&](int i) -> uint32_t {
-        if ((i & 3) == 0) r = rng.next<7>();
-        const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-        const uint32_t j = (uint32_t)i + below(word, (uint32_t)(kCards - i));
+        if ((i & 7) == 0) r = rng.next<7>();
+        uint32_t off;
+        if ((i & 1) == 0) {
+            spare = (i & 7) == 0 ? r.x : (i & 7) == 2 ? r.y : (i & 7) == 4 ? r.z : r.w;   // i is a compile-time constant after unrolling
+            off = below_keep(spare, (uint32_t)(kCards - i));
+        } else {
+            off = below(spare, (uint32_t)(kCards - i));
+        }
+        const uint32_t j = (uint32_t)i + off;
         const uint32_t card = deck[j];
         deck[j] = deck[i];   // position i is never read again, so only half of the swap is needed
         return card;
