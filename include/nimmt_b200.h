@@ -19,14 +19,19 @@
  *     the only values any reference caller uses (agents/mcts.py:21-23, play.py:17).
  *   - num_players P in [1, 10] (env.py:19-21: 10 P + 4 <= 104).
  *
- * Packed game state (HBM layout).  For a batch of B games:
- *     uint4 hand[P][B]   128-bit word per (player, game): bits 0..103 = cards held,
- *                        bits 120..127 = that player's cumulative Hornochsen (<= 171)
- *     uint4 rows_a[B]    bytes 0..15 of the 24-byte row block
- *     uint2 rows_b[B]    bytes 16..23 of the row block
- *   row block = 4 rows x 6 bytes: 5 card slots (oldest first) + 1 meta byte
- *   (bits 0..2 = cards in the row, bits 3..7 = bull-head sum of the row, <= 27).
- *   Total (16 P + 24) B bytes, structure-of-arrays so that a warp's accesses are contiguous.
+ * Packed game state (HBM layout).  A hand only ever loses one card per step, so the ten cards a
+ * player was dealt are stored once and a step writes one 32-bit word per player.  Games are stored in tiles of 32:
+ *     uint2    cards[tile][P][32]   bytes 0..7 = the cards of hand slots 0..7, ascending (0xFF = none);
+ *                                   written by deal / reset_to only
+ *     per tile, contiguous:
+ *       uint32 meta[P][32]          bits 0..9 slot empty (played or never dealt), bits 10..17 the player's
+ *                                   cumulative Hornochsen (<= 171), bits 18..24 / 25..31 cards of slots 8 / 9
+ *                                   (127 = none)
+ *       uint8  rows[32][24]         row record, slot-major: byte 4 j + r = j-th card (oldest first) of row r,
+ *                                   j = 0..4; byte 20 + r = cards in the row (bits 0..2) | bull-head sum of the
+ *                                   row (bits 3..7, <= 27)
+ *   Total ceil(B / 32) * 32 * (12 P + 24) bytes.  A warp's accesses are contiguous in every plane and a tile is
+ *   three contiguous runs of HBM.
  */
 #ifndef NIMMT_B200_H
 #define NIMMT_B200_H
@@ -68,7 +73,7 @@ NIMMT_API int nimmt_abi_version(void);
 /* Text of the last CUDA error seen by this thread's calls ("" if none). */
 NIMMT_API const char *nimmt_last_cuda_error(void);
 
-/* Bytes of packed state for B games of P players: (16 P + 24) B.  Replaces the list
+/* Bytes of packed state for B games of P players: (12 P + 24) bytes per game, whole tiles of 32 games.  Replaces the list
  * allocations of SechsNimmtEnv.__init__ (env.py:30-32). Returns 0 on bad arguments. */
 NIMMT_API size_t nimmt_state_bytes(int64_t num_games, int num_players);
 

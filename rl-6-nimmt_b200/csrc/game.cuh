@@ -1,7 +1,7 @@
 // game.cuh — device-side primitives of the 6 nimmt! hot path (sm_100a).
 //
-// Everything here is register-resident integer code: a game is P 128-bit hand words plus a
-// 24-byte row block (include/nimmt_b200.h).  No dynamic register indexing: every
+// Everything here is register-resident integer code: card sets as 128-bit words, rows as two comparison keys
+// per row plus a 24-byte record; handrec.cuh adds the stored form of a hand (include/nimmt_b200.h).  No dynamic register indexing: every
 // data-dependent row / player choice is a predicated select, so nothing spills to local memory
 // and a warp of 32 independent games never diverges inside a placement.
 //
