@@ -415,12 +415,32 @@ def run_ours(args):
         t = torch.tensor([puct_ms, leaf_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         puct_ms, leaf_ms = float(t[0]), float(t[1])
+    # the whole self-play loop of configs[3]: 256 games, four PUCT seats sharing one net (mc_max = 200, run.py), every
+    # search on chip, one batched imitation step per iteration
+    from rl_6_nimmt_b200.play import BatchedGameSession, PolicySeat
+    torch.manual_seed(0)
+    sp_net = PL.PolicyNet()
+    session = BatchedGameSession([PolicySeat(sp_net, mc_max=200, puct=True, learn=True) for _ in range(P)], 256, device=dev, seed=7)
+    session.play_games()
+    barrier()
+    a0.record()
+    for r in range(2):
+        session.play_games()
+    a1.record()
+    barrier()
+    selfplay_ms = a0.elapsed_time(a1) / 2
+    if world > 1:
+        t = torch.tensor([selfplay_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        selfplay_ms = float(t.item())
     rows_per_rollout = P * sum(range(1, 11))           # 220 policy rows in a full 4-player rollout
     flop_per_row = 2 * (48 * 100 + 100 * 100 + 100)    # un-padded, SURVEY.md §8d
     alpha = {
         "puct_rollouts_per_sec": world * 256 * 200 / (puct_ms * 1e-3), "ms_per_256_decisions": puct_ms,
         "config": "256 PUCT searches per GPU (4-player opening roots, 10 legal cards), 200 sequential rollouts each, random-init policy net (torch.manual_seed(0))",
         "policy_tflops_in_search": world * 256 * 200 * rows_per_rollout * flop_per_row / (puct_ms * 1e-3) / 1e12,
+        "selfplay_games_per_sec": world * 256 / (selfplay_ms * 1e-3), "selfplay_ms_per_256_games": selfplay_ms,
+        "selfplay_config": "256 four-player games per GPU, every seat a PUCT agent (mc_max 200) on one shared net, 36 search launches + one batched imitation step (Adam) per iteration",
         "leaf_eval_decisions_per_sec": world * (1 << 20) / (leaf_ms * 1e-3),
         "leaf_eval_tflops": world * float((obs_all[:, :10] >= 0).sum()) * flop_per_row / (leaf_ms * 1e-3) / 1e12,
     }

@@ -247,8 +247,9 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
                 const uint32_t bits = __float_as_uint(logit + gumbel);
                 const int ordered = (int)(bits ^ ((uint32_t)((int)bits >> 31) >> 1));
                 const int key = playing && slot < h ? (ordered & ~15) | (15 - slot) : INT_MIN;
-                const uint32_t members = dloc < kDecPerWarp ? 0x3FFu << gbase : 0xC0000000u;   // the ten lanes of this decision
-                const int winner = __reduce_max_sync(members, key);
+                int winner = INT_MIN;   // ten independent shuffles + a max tree (a redux.sync per decision serialises over the masks)
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) winner = max(winner, __shfl_sync(kFull, key, gbase + s));
                 if (pick < 0) pick = 15 - (winner & 15);
             }
             // ---- hand.remove(card): the lanes behind the pick shift down by one ----
