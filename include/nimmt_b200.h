@@ -21,7 +21,7 @@
  *
  * Packed game state (HBM layout).  A hand only ever loses one card per step, so the ten cards a
  * player was dealt are stored once and a step writes one 32-bit word per player.  Games are stored in tiles of 32:
- *     uint2    cards[tile][P][32]   bytes 0..7 = the cards of hand slots 0..7, ascending (0xFF = none);
+ *     uint2    cards[tile][P][32]   bytes 0..7 = the cards of hand slots 0..7, ascending (0x7F = none);
  *                                   written by deal / reset_to only
  *     per tile, contiguous:
  *       uint32 meta[P][32]          bits 0..9 slot empty (played or never dealt), bits 10..17 the player's

@@ -5,7 +5,7 @@
 // once (by the deal) and never again; a step reads them to find the slot of the played card and writes back one
 // 32-bit word per player — ten "slot is empty" bits plus the running Hornochsen score — instead of a 128-bit set:
 //
-//     uint2    lo      bytes 0..7: the cards of slots 0..7, ascending; 0xFF = no card was dealt to the slot
+//     uint2    lo      bytes 0..7: the cards of slots 0..7, ascending; 0x7F = no card was dealt to the slot
 //     uint32_t meta    bits  0..9   slot i is empty (played, or never dealt)
 //                      bits 10..17  Hornochsen taken so far (<= 171)
 //                      bits 18..24  card of slot 8, bits 25..31 card of slot 9 (127 = none) — immutable, they
@@ -46,32 +46,33 @@ NIMMT_HD uint32_t rec_card(const HandRec& h, int slot) {
     return slot < 8 ? low : high;
 }
 
-// Flags (bit 7 of each byte) the bytes of `w` that equal the byte replicated in `pattern`.  Bits above the
-// lowest flag may be spurious (borrow), so callers use the lowest flag only; cards in a hand are distinct.
-NIMMT_HD uint32_t eq_byte_flags(uint32_t w, uint32_t pattern) {
-    const uint32_t x = w ^ pattern;
-    return (x - 0x01010101u) & ~x & 0x80808080u;
+// One-hot slot mask of `card` (bit i = slot i was dealt that card), 0 if the hand never held it.  Valid for card < 104;
+// larger ids may return garbage and are rejected by the caller.  Branch-free and mostly multiplies, which run on the
+// FMA pipe while the rest of a step saturates the ALU pipe:
+//   * all stored bytes and the pattern bytes are < 0x80, so (x + 0x7F) sets bit 7 of a byte iff the byte is non-zero and
+//     never carries into its neighbour: ~(x + 0x7F7F7F7F) & 0x80808080 flags exactly the equal bytes;
+//   * the high word of flags * (2^25 + 2^18 + 2^11 + 2^4) has the flag of byte i at bit i (stray partial products land
+//     at bits >= 8; at most one flag is set because the cards of a hand are distinct).
+NIMMT_HD uint32_t rec_slot_bit(const HandRec& h, uint32_t card) {
+    const uint32_t pattern = card * 0x01010101u;
+    const uint32_t f0 = ~((h.lo.x ^ pattern) + 0x7F7F7F7Fu) & 0x80808080u;
+    const uint32_t f1 = ~((h.lo.y ^ pattern) + 0x7F7F7F7Fu) & 0x80808080u;
+    const uint32_t low = (umulhi32(f0, 0x02040810u) | umulhi32(f1, 0x20408100u)) & 0xFFu;
+    const uint32_t x2 = (h.meta >> 18) ^ (card * 129u);   // the two 7-bit fields against card | card << 7
+    const uint32_t s8 = (x2 & 0x7Fu) == 0u ? 0x100u : 0u, s9 = (x2 & 0x3F80u) == 0u ? 0x200u : 0u;
+    return low | s8 | s9;
 }
 
-// Slot holding `card`, or -1 (card ids >= 104 never match: stored "none" bytes are 0xFF / 127).
+// Slot holding `card`, or -1.
 NIMMT_HD int rec_find(const HandRec& h, uint32_t card) {
-    const uint32_t pattern = (card & 0xFFu) * 0x01010101u;
-    const uint32_t f0 = eq_byte_flags(h.lo.x, pattern), f1 = eq_byte_flags(h.lo.y, pattern);
-    int slot = -1;
-    slot = ((h.meta >> 25) & 127u) == card ? 9 : slot;
-    slot = ((h.meta >> 18) & 127u) == card ? 8 : slot;
-    slot = f1 ? 4 + ((ffs32(f1) - 1) >> 3) : slot;
-    slot = f0 ? (ffs32(f0) - 1) >> 3 : slot;
-    return card < (uint32_t)kCards ? slot : -1;
+    return card < (uint32_t)kCards ? ffs32(rec_slot_bit(h, card)) - 1 : -1;
 }
 
 // env.py:114-118 + :131 — if `card` is in the hand, marks its slot empty in `meta` and returns true.
 NIMMT_HD bool rec_take(const HandRec& h, uint32_t card, uint32_t& meta) {
-    const int slot = rec_find(h, card);
-    const uint32_t bit = slot >= 0 ? 1u << slot : 0u;
-    const bool held = bit != 0u && (h.meta & bit) == 0u;
-    meta = h.meta | (held ? bit : 0u);
-    return held;
+    const uint32_t bit = rec_slot_bit(h, card) & ~h.meta;   // the slot must still hold its card
+    meta = h.meta | bit;                                    // only committed by the caller if every move is legal
+    return bit != 0u && card < (uint32_t)kCards;
 }
 
 // Card of the k-th (0-based) unplayed slot = the k-th smallest card in hand; k < rec_count(h).
@@ -91,7 +92,7 @@ NIMMT_HD uint4 rec_to_mask(const HandRec& h) {
 NIMMT_HD HandRec rec_from_sorted(const uint32_t (&cards)[kHand], int n, uint32_t score) {
     uint32_t c[kHand];
 #pragma unroll
-    for (int i = 0; i < kHand; ++i) c[i] = i < n ? cards[i] : 0xFFu;
+    for (int i = 0; i < kHand; ++i) c[i] = i < n ? cards[i] : kNoCard7;
     HandRec h;
     h.lo.x = c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24);
     h.lo.y = c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24);
