@@ -156,27 +156,27 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
                 if (slot < 5) reinterpret_cast<uint4*>(&ts.cur)[slot] = reinterpret_cast<const uint4*>(&ts.root)[slot];
             }
             // partial Fisher-Yates over the unseen cards, the first (P-1) n entries become the opponents' hands:
-            // the swap targets are drawn in parallel (one per row), the swaps run on one thread below
+            // the swap targets are drawn in parallel (one per row) and resolved in parallel below
             const int i = player * kSlots + slot;
             if (i < need) {
                 Philox rng(seed, rollout_id, 0x6465616cu, (uint32_t)i);
-                ts.draw[i] = (uint8_t)(i + (int)below(rng.next().x, (uint32_t)(n_avail - i)));
+                ts.draw[i] = (uint8_t)(i + (int)below(rng.next().x, (uint32_t)(n_avail - i)));   // swap target k_i of Fisher-Yates step i
             }
         }
         int outcome = 0, first_index = -1;
         rk = rk_root;
         __syncthreads();
-        if (is_tree && tree_ok) {
-            for (int i = 0; i < need; ++i) {
-                const int k = ts.draw[i];
-                const uint8_t a = ts.deck[i], b = ts.deck[k];
-                ts.deck[i] = b; ts.deck[k] = a;
-            }
-        }
-        __syncthreads();
-        {   // each opponent sorts its chunk (mcts.py:124): rank sort across the decision's ten lanes
+        {   // Resolve the shuffle without running it: draw i takes what sits at position k_i after swaps 0..i-1.  Position p
+            // holds its original card unless an earlier swap j (the latest with k_j == p) moved position j's content there,
+            // and so on back — a walk over j = i-1 .. 0 that every row does for its own draw in parallel, instead of a chain
+            // of (P-1) n dependent shared-memory swaps on one thread.  The deck itself is never modified.  Then each opponent
+            // sorts its chunk (mcts.py:124): rank sort across the decision's ten lanes.
             const bool opp = tree_ok && player > 0;
-            const int v = opp && slot < root_n ? (int)ts.deck[(player - 1) * root_n + slot] : 127;
+            const int i = (player - 1) * root_n + slot;          // this row's draw: opponent `player`, card `slot` of its chunk
+            int v = 127;
+            if (opp && slot < root_n) {
+                v = (int)ts.deck[fisher_yates_source<(P - 1) * kHand>(ts.draw, i)];
+            }
             int rank = 0;
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) rank += __shfl_sync(kFull, v, gbase + s) < v;

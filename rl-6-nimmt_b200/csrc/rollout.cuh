@@ -78,6 +78,17 @@ NIMMT_HD bool make_rollout_root(const nimmt_root& root, const uint8_t* values, R
     return true;
 }
 
+// Fisher-Yates without running it.  Step i of the shuffle swaps positions i and k_i = target[i] >= i and outputs what
+// then sits at position i.  Position p holds its original entry unless an earlier step j (the latest with k_j == p) moved
+// position j's content there, and so on back: walking j = i-1 .. 0 gives the ORIGINAL position whose entry step i outputs.
+// Every step can be resolved independently (one thread each) and the array is never modified.
+template <int MAX_STEPS>
+NIMMT_HD int fisher_yates_source(const uint8_t* target, int i) {
+    int pos = target[i];
+    for (int j = MAX_STEPS - 1; j >= 0; --j) pos = (j < i && (int)target[j] == pos) ? j : pos;
+    return pos;
+}
+
 // The opponents' cards of one turn: player p draws the next card of the shrinking pool (compile-time recursion so that
 // every draw knows which half of which random word it consumes).
 template <int P, int I>

@@ -86,3 +86,12 @@ def puct(legal, outcomes, probs, c_puct=2.0):
     pucts = np.zeros(len(legal), np.float64)
     choice = lib().sim_puct(len(legal), len(out), _p(idx), _p(out), _p(probs), ctypes.c_float(c_puct), _p(pucts))
     return choice, pucts
+
+
+def fisher_yates_sources(targets):
+    """targets[i] = swap partner of step i (>= i).  Returns the original position each step's output comes from."""
+    t = np.zeros(90, np.uint8)
+    t[: len(targets)] = targets
+    out = np.zeros(len(targets), np.int32)
+    lib().sim_fisher_yates_sources(_p(t), len(targets), _p(out))
+    return out

@@ -187,6 +187,10 @@ int sim_random_actions(int P_, int n, const int8_t* rows0, const int8_t* hands0,
     return 0;
 }
 void sim_set_form(int form) { g_form = form; }
+// source[i] = original position of the entry that Fisher-Yates step i outputs, for steps 0..n-1 (n <= 90)
+void sim_fisher_yates_sources(const uint8_t* target, int n, int* source) {
+    for (int i = 0; i < n; ++i) source[i] = fisher_yates_source<90>(target, i);
+}
 int sim_check_sort_networks() {
     int bad = 0;
     bad |= check_network<2>(); bad |= check_network<3>(); bad |= check_network<4>(); bad |= check_network<5>();

@@ -98,3 +98,20 @@ def test_puct_rule_matches_reference_cases():
                 assert abs(got - want) < 1e-12, (got, want)
         assert choice == c["choice"]
     assert n_nan > 0
+
+
+def test_fisher_yates_resolved_without_swapping():
+    """rollout.cuh::fisher_yates_source (the policy rollouts deal the opponents with it, one thread per draw) against a
+    shuffle that really swaps."""
+    from host_sim import fisher_yates_sources
+    rng = np.random.RandomState(8)
+    for _ in range(300):
+        n_avail = int(rng.randint(1, 95))
+        steps = int(rng.randint(1, min(n_avail, 90) + 1))
+        targets = np.array([i + rng.randint(n_avail - i) for i in range(steps)], np.uint8)
+        deck = list(range(n_avail))
+        want = []
+        for i, k in enumerate(targets):
+            deck[i], deck[k] = deck[k], deck[i]
+            want.append(deck[i])
+        assert fisher_yates_sources(targets).tolist() == want
