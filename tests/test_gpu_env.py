@@ -262,3 +262,28 @@ def test_step_host_matches_step_with_byte_and_bit_done():
                 assert not np.unpackbits(h_bits.numpy().view(np.uint8), bitorder="little")[B:].any()
             assert (h_rew.numpy() == rew.cpu().numpy()).all() and (got_done == done.cpu().numpy()).all(), (B, t)
         assert got_done.all() and torch.equal(a_env.state, b_env.state)
+
+
+@pytest.mark.parametrize("P", (2, 4, 7, 10))
+def test_reset_to_midgame_positions_from_the_golden_traces(P):
+    """reset_to with short hands (the MC agents' roots, agents/mcts.py:108-114): every golden game is re-entered at turns
+    3, 7 and 9 — hands of 7, 3 and 1 cards, listed in DESCENDING order to show that the stored record does not depend on
+    the caller's order — and played on; rewards, done, hands, boards and observations must match the reference's
+    trace from there on (scores restart at zero, env.py:58)."""
+    z = np.load(os.path.join(GOLDEN, "env_traces.npz"))
+    g = lambda k: z[f"p{P}_{k}"]
+    for t0 in (3, 7, 9):
+        hands0 = g("hands")[:, t0].copy()                       # state after t0 steps: [n, P, 10], -1 padded
+        shuffled = -np.ones_like(hands0)
+        for idx in np.ndindex(hands0.shape[:2]):
+            cards = hands0[idx][hands0[idx] >= 0][::-1]
+            shuffled[idx][: len(cards)] = cards
+        out, first = _replay_gpu(P, g("boards")[:, t0], shuffled, g("actions")[:, t0:])
+        assert not out["illegal"].any()
+        assert (first == g("obs")[:, t0]).all()
+        for k in ("rewards", "done"):
+            assert (out[k] == g(k)[:, t0:]).all(), (k, t0)
+        for k in ("hands", "boards", "obs"):
+            assert (out[k] == g(k)[:, t0 + 1:]).all(), (k, t0)
+        base = g("scores")[:, t0][:, None, :]
+        assert (out["scores"] == g("scores")[:, t0 + 1:] - base).all()
