@@ -388,6 +388,28 @@ def run_ours(args):
         mcs_ms = float(t.item())
     mcs_value = world * reps * 256 * 10 * per_action / (mcs_ms * 1e-3)
 
+    # BASELINE configs[2] itself: ONE decision batch (the same roots on every rank), 10,000 rollouts per candidate card,
+    # rollout ids striped over the ranks, then the path's only collective (int64 [D,10,3] all-reduce over NCCL / NVLink)
+    shard_obs = BatchedSechsNimmtEnv(4096, P, seed=6, game0=0).reset().observe(dtype=torch.int8).cpu().numpy()
+    shard_roots = torch.as_tensor(np.stack([R.pack_root([[int(c) for c in row if c >= 0] for row in o[0, -24:].reshape(4, 6)], [int(c) for c in o[0, :10]],
+                                  [c for c in range(104) if c not in set(o[0, :10].tolist()) | set(o[0, -24:].tolist())], P) for o in shard_obs])).to(dev)
+    sharded = {}
+    for D, reps_d in ((1, 20), (4096, 2)):
+        R.sharded_mcs_rollouts(shard_roots[:D], P, 10_000, seed=1, device=dev)
+        barrier()
+        m0.record()
+        for r in range(reps_d):
+            table = R.sharded_mcs_rollouts(shard_roots[:D], P, 10_000, seed=2 + r, device=dev)
+        m1.record()
+        barrier()
+        ms_d = m0.elapsed_time(m1) / reps_d
+        if world > 1:
+            t = torch.tensor([ms_d], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_d = float(t.item())
+        assert int(table[:, :, 2].sum()) == D * 10 * 10_000       # every rollout of every candidate was played exactly once
+        sharded[f"D{D}"] = {"ms_per_decision_batch": ms_d, "rollouts_per_sec": D * 10 * 10_000 / (ms_d * 1e-3)}
+
     # ---- Alpha0.5 (BASELINE configs[3]): 256 PUCT searches per GPU, 200 rollouts each, policy net on tcgen05 ----
     from rl_6_nimmt_b200 import policy as PL
     torch.manual_seed(0)
@@ -475,7 +497,7 @@ def run_ours(args):
                  "fused_random_play_env_steps_per_sec": world * B / (fused_ms * 1e-3),
                  "fused_note": "k_step<4,true>: actions drawn in-kernel, + k_deal every 10th visit; per-rank ms, not max-reduced"},
         "alpha05": alpha,
-        "mcs": {"metric": "mcs_rollouts_per_sec", "value": mcs_value, "unit": "rollouts/s",
+        "mcs": {"metric": "mcs_rollouts_per_sec", "value": mcs_value, "sharded_decision_10k_per_card": sharded, "unit": "rollouts/s",
                 "config": "256 four-player opening roots x 10 candidate cards x 2000 rollouts per launch, 5 launches"},
     }
     if world == 1 and not args.no_cpu_baseline:
