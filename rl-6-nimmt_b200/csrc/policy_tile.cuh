@@ -94,6 +94,8 @@ struct PhaseClock {
 __device__ __forceinline__ void init_feature_constants(uint8_t* gbuf, int row) {
     *reinterpret_cast<uint4*>(gbuf + kGA1 + canon_off(row, kBiasCol, kInChunks)) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // 1.0, 1.0, 0 ..
     *reinterpret_cast<uint4*>(gbuf + kGA1 + canon_off(row, kBiasCol + 8, kInChunks)) = make_uint4(0u, 0u, 0u, 0u);
+    // layer 2's A operand, k = 104..111: hidden units that do not exist.  The epilogue never reads or writes them.
+    *reinterpret_cast<uint4*>(gbuf + kGA2 + canon_off(row, kHidPad - 8, kHidChunks)) = make_uint4(0u, 0u, 0u, 0u);
 }
 // Chunk c (features 8 c .. 8 c + 7, bf16) of one row of the layer-1 A operand.
 __device__ __forceinline__ void store_feature_chunk(uint8_t* gbuf, int row, int c, uint4 v) {
@@ -175,8 +177,18 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     tc_fence_after_sync();
     pc.mark(2);
     // epilogue 1: ReLU, round to bf16, store as layer 2's A operand (4 + 3 chunks bound the live registers)
+    // TMEM reads are the scarce resource of this tile (64 B/clk per SM): only the 104 columns that exist are read
     epilogue1_chunks<0, 4>(lane_taddr, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
-    epilogue1_chunks<4, kHidPad / 16>(lane_taddr, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
+    epilogue1_chunks<4, 6>(lane_taddr, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
+    {
+        uint32_t v[8];   // units 96..103 (100, 101 are the constant-1 units that carry b2)
+        tmem_ld8(lane_taddr + 96, v);
+        tmem_ld_wait();
+        uint32_t packed[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) packed[i] = relu_pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        *reinterpret_cast<uint4*>(gbuf + kGA2 + canon_off(row, 96, kHidChunks)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
     // ---- layer 2 ----
     fence_async_smem();
     tc_fence_before_sync();
@@ -197,7 +209,14 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     // epilogue 2 + layer 3: logit = w3 . relu(acc) + b3, fp32
     float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     epilogue2_chunks<0, 4>(lane_taddr, w3, part);
-    epilogue2_chunks<4, kHidPad / 16>(lane_taddr, w3, part);
+    epilogue2_chunks<4, 6>(lane_taddr, w3, part);
+    {
+        uint32_t v[4];   // units 96..99: the last ones that exist
+        tmem_ld4(lane_taddr + 96, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) part[i] = fmaf(fmaxf(__uint_as_float(v[i]), 0.0f), w3[96 + i], part[i]);
+    }
     const float logit = b3 + ((part[0] + part[1]) + (part[2] + part[3]));
     tc_fence_before_sync();      // ordered before the caller's next barrier / the next tile's MMA
     pc.mark(6);
