@@ -182,3 +182,52 @@ def test_alpha05_agent_dropin_plays_and_learns():
     key = agent._packed_key
     agent._weights()
     assert agent._packed_key != key                    # weights were repacked after the update
+
+
+@pytest.mark.parametrize("P", (1, 2, 3, 5, 6, 10))
+def test_policy_rollouts_other_table_sizes_vs_oracle(P):
+    """The kernel packs floor(12 / P) trees into a CTA and maps rows (decision, slot) three decisions per warp; this runs
+    every packing (12, 6, 4, 2, 2, 1 trees per CTA) on mid-game roots and z-tests the per-card outcome means against the
+    fp32 C oracle of the reference's PolicyMCSAgent rollouts (sharpened policy).  Also: roots of different hand sizes in
+    one launch, and more roots than fit one CTA."""
+    from rl_6_nimmt_b200.env import BatchedSechsNimmtEnv
+    z, net, w = _rollout_golden()
+    blob = PL.pack_weights(net)
+    n_roots = 7
+    env = BatchedSechsNimmtEnv(n_roots, P, seed=40 + P).reset()
+    roots, metas = [], []
+    # play a different number of turns per game by stepping everything and snapshotting game g after 2 + (g % 4) turns
+    snaps = {}
+    for t in range(6):
+        obs = env.observe(dtype=torch.int8).cpu().numpy()
+        for g in range(n_roots):
+            if t == 2 + (g % 4):
+                snaps[g] = obs[g].copy()
+        env.step(env.random_actions().clone())
+    for g in range(n_roots):
+        o = snaps[g]
+        board = [[int(c) for c in row if c >= 0] for row in o[0, -24:].reshape(4, 6)]
+        own = [int(c) for c in o[0, :10] if c >= 0]
+        seen = set(own) | {c for row in board for c in row}
+        avail = [c for c in range(104) if c not in seen]            # a fresh agent's memory: everything not visible
+        roots.append(R.pack_root(board, own, avail, P))
+        metas.append((board, own, avail))
+    n_per_card = 1500
+    stats, _ = R.policy_rollouts(np.stack(roots), P, blob, 8 * n_per_card, root_rule=N.ROOT_STRATIFIED, seed=9)   # hands hold <= 8 cards
+    stats = stats.cpu().numpy()
+    for g, (board, own, avail) in enumerate(metas):
+        n = len(own)
+        got = stats[g]
+        want = oracle.policy_rollouts(P, board, own, avail, n * (1200 if P <= 5 else 500), w, seed=3 + g)
+        for i in range(n):
+            s, ss, cnt = (int(x) for x in got[i])
+            ws, wss, wn = (int(x) for x in want[i])
+            # every root plays its own budget: n_mc is per launch, so smaller hands get at least n_per_card per card too
+            assert cnt >= n_per_card and wn > 0
+            mean, var = s / cnt, max(ss / cnt - (s / cnt) ** 2, 1e-9)
+            wmean, wvar = ws / wn, max(wss / wn - (ws / wn) ** 2, 1e-9)
+            zscore = (mean - wmean) / np.sqrt(var / cnt + wvar / wn)
+            assert abs(zscore) < 5.0, (P, g, i, mean, wmean, zscore)
+        assert (got[n:] == 0).all()
+        if g >= 1:
+            break                                                    # two roots per table size keep the oracle's CPU time short
