@@ -69,9 +69,14 @@ class BatchedGameSession:
         self.env = BatchedSechsNimmtEnv(num_games, len(self.seats), device=device, seed=seed)
         self.lib, self.seed = N.lib(), int(seed)
         B, dev = num_games, self.env.device
-        self._roots = torch.zeros((B, R.ROOT_BYTES), dtype=torch.uint8, device=dev)
-        self._stats = torch.zeros((B, R.MAX_ACTIONS, 3), dtype=torch.int64, device=dev)
-        self._available = {p: torch.zeros((B, 16), dtype=torch.uint8, device=dev) for p, s in enumerate(self.seats) if isinstance(s, MCSSeat)}
+        # every searching seat has its own buffers and its own stream: the seats' searches of one turn are independent
+        # (each reads the state and writes its own column of the action matrix), and a latency-bound search kernel
+        # (k_policy_rollouts: one CTA per few trees, four warps) leaves most of an SM idle for the next seat's CTAs
+        mc = [p for p, s in enumerate(self.seats) if isinstance(s, MCSSeat)]
+        self._roots = {p: torch.zeros((B, R.ROOT_BYTES), dtype=torch.uint8, device=dev) for p in mc}
+        self._stats = {p: torch.zeros((B, R.MAX_ACTIONS, 3), dtype=torch.int64, device=dev) for p in mc}
+        self._available = {p: torch.zeros((B, 16), dtype=torch.uint8, device=dev) for p in mc}
+        self._streams = {p: torch.cuda.Stream(device=dev) for p in mc}
         self._generator = torch.Generator(device=dev)
         self._generator.manual_seed(self.seed)
         self.results = []   # one int32 [B, P] tensor of (negative) totals per play_games() call
@@ -110,20 +115,25 @@ class BatchedGameSession:
                     slot = probs.argmax(dim=1, keepdim=True) if seat.greedy else torch.multinomial(probs, 1, generator=self._generator)
                     actions[:, p] = mine[:, :10].gather(1, slot).squeeze(1).to(torch.uint8)
                     continue
-                with torch.cuda.device(env.device):
-                    N.check(self.lib.nimmt_mc_roots(N.ptr(env.state), N.ptr(self._available[p]), N.ptr(self._roots), B, P, p,
-                                                    int(turn == 0), self._stream()), "nimmt_mc_roots")
-                    self._stats.zero_()
+                main, side = torch.cuda.current_stream(env.device), self._streams[p]
+                side.wait_stream(main)                               # the state and the action matrix are ready
+                with torch.cuda.device(env.device), torch.cuda.stream(side):
+                    roots, stats = self._roots[p], self._stats[p]
+                    N.check(self.lib.nimmt_mc_roots(N.ptr(env.state), N.ptr(self._available[p]), N.ptr(roots), B, P, p,
+                                                    int(turn == 0), side.cuda_stream), "nimmt_mc_roots")
+                    stats.zero_()
                     seed = (self.seed * 1000003 + self.games * 131 + turn * 17 + p) & (2**64 - 1)
                     if n_cards > 1:                                # a single card is played without search (agents/mcts.py:52-53)
                         if isinstance(seat, PolicySeat):
-                            stats, _ = R.policy_rollouts(self._roots, P, seat.weights, seat.n_mc(n_cards), c_puct=seat.c_puct,
+                            found, _ = R.policy_rollouts(roots, P, seat.weights, seat.n_mc(n_cards), c_puct=seat.c_puct,
                                                          root_rule=seat.root_rule, seed=seed, device=env.device)
-                            self._stats.copy_(stats)
+                            stats.copy_(found)
                         else:
-                            R.mcs_rollouts(self._roots, P, seat.per_card(n_cards), seed=seed, out=self._stats, device=env.device)
-                    N.check(self.lib.nimmt_mc_choose(N.ptr(env.state), N.ptr(self._stats), N.ptr(actions), B, P, p, self._stream()),
+                            R.mcs_rollouts(roots, P, seat.per_card(n_cards), seed=seed, out=stats, device=env.device)
+                    N.check(self.lib.nimmt_mc_choose(N.ptr(env.state), N.ptr(stats), N.ptr(actions), B, P, p, side.cuda_stream),
                             "nimmt_mc_choose")
+            for side in self._streams.values():                      # join: every seat has written its column
+                torch.cuda.current_stream(env.device).wait_stream(side)
             if learning:
                 obs = env.observe(dtype=torch.int8)
                 for p in learning:
