@@ -79,9 +79,13 @@ def run(P, B):
     assert all(int(e.illegal.any()) == 0 for e in envs)
     deals()
     ms_ra = graph_time(lambda: [e.random_actions(out=tp[0], turn=0) for e, tp in zip(envs, tapes)]) / nsets
-    obs8 = torch.empty((B, P, 47), dtype=torch.int8, device="cuda")
-    ms_obs8 = graph_time(lambda: [e.observe(out=obs8) for e in envs]) / nsets
-    out["k_step_ms"], out["k_deal_ms"], out["k_random_actions_ms"], out["k_observe_i8_ms"] = ms_step, ms_deal, ms_ra, ms_obs8
+    out["k_step_ms"], out["k_deal_ms"], out["k_random_actions_ms"] = ms_step, ms_deal, ms_ra
+    obs8 = None
+    if B * P * 47 <= 40e9:   # the int8 observations of 2^28 ten-player games alone would be 126 GB
+        obs8 = torch.empty((B, P, 47), dtype=torch.int8, device="cuda")
+        ms_obs8 = graph_time(lambda: [e.observe(out=obs8) for e in envs]) / nsets
+        out["k_observe_i8_ms"] = ms_obs8
+        out["observe_i8_GBs"] = (12 * P + 24 + 47 * P) * B / (ms_obs8 * 1e-3) / 1e9
     if B * P * 47 * 4 <= 24e9:
         obs32 = torch.empty((B, P, 47), dtype=torch.float32, device="cuda")
         out["k_observe_f32_ms"] = graph_time(lambda: [e.observe(out=obs32) for e in envs]) / nsets
@@ -93,7 +97,6 @@ def run(P, B):
     out["step_algorithmic_GBs"] = alg * B / (ms_step * 1e-3) / 1e9
     out["step_frac_of_measured_hbm_peak"] = out["step_algorithmic_GBs"] / PEAK
     out["deal_GBs"] = (12 * P + 24) * B / (ms_deal * 1e-3) / 1e9
-    out["observe_i8_GBs"] = (12 * P + 24 + 47 * P) * B / (ms_obs8 * 1e-3) / 1e9
     del envs, tapes, obs8
     torch.cuda.empty_cache()
     return out
@@ -102,9 +105,11 @@ def run(P, B):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-log2", type=int, default=26)
+    ap.add_argument("--min-log2", type=int, default=20)
+    ap.add_argument("--players", type=int, nargs="*", default=[10, 4, 2])
     args = ap.parse_args()
-    for P in (10, 4, 2):
+    for P in args.players:
         for lg in (20, 22, 24, 26, 28):
-            if lg > args.max_log2 or (12 * P + 24 + 20 * P) * (1 << lg) * min(4, max(1, 400_000_000 // ((12 * P + 24) << lg) + 1)) > 120e9:
+            if lg < args.min_log2 or lg > args.max_log2 or (12 * P + 24 + 20 * P) * (1 << lg) * min(4, max(1, 400_000_000 // ((12 * P + 24) << lg) + 1)) > 120e9:
                 continue
             print(json.dumps(run(P, 1 << lg)), flush=True)
