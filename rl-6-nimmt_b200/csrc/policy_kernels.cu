@@ -156,7 +156,18 @@ int nimmt_policy_pack_weights(const float* w1, const float* b1, const float* w2,
         split(b2[n], hi, lo);
         put2(n, kOneUnit, hi);
         put2(n, kOneUnit + 1, lo);
-        w3p[n] = w3[n];
+        w3p[n] = 0.5f * w3[n];                 // the |h| half of relu(h) = (h + |h|) / 2
+    }
+    // the linear half, sum_n (w3_n / 2) h_n, as output units 100 (hi) and 101 (lo) of layer 2: the combined row is formed
+    // from the bf16 weights the tensor core really multiplies by, bias columns included
+    for (int k = 0; k < kOneUnit + 2; ++k) {
+        double acc = 0.0;
+        for (int n = 0; n < kHid; ++n)
+            acc += 0.5 * (double)w3[n] * (double)bf16_to_float(*reinterpret_cast<const uint16_t*>(blob + kOffW2 + canon_off(n, k, kHidChunks)));
+        uint16_t hi, lo;
+        split((float)acc, hi, lo);
+        put2(kOneUnit, k, hi);
+        put2(kOneUnit + 1, k, lo);
     }
     put1(kOneUnit, kBiasCol, 0x3F80);       // units 100, 101 of layer 1: relu(1 * 1) = 1, the inputs that carry b2
     put1(kOneUnit + 1, kBiasCol, 0x3F80);

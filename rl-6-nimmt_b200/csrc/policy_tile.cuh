@@ -5,7 +5,8 @@
 // built to keep the threads' share small:
 //   * biases ride in the GEMMs: features 48, 49 of every row are the constant 1 and carry b1 split into two
 //     bf16 terms (hi + lo, ~16 mantissa bits); layer 1's units 100, 101 are the constant 1 and carry b2 the
-//     same way.  Epilogue 1 is cvt.relu.bf16x2 + store, epilogue 2 is max + fma per column.
+//     same way.  Epilogue 1 is cvt.relu.bf16x2 + store; epilogue 2 is ONE fma per column, because the linear half
+//     of the ReLU head is computed by the GEMM as well (epilogue2_chunks).
 //   * feature rows are assembled from bf16 data that is already laid out in 16-byte chunks (six vector
 //     loads and stores per row) instead of 48 scalar conversions.
 #pragma once
@@ -124,7 +125,10 @@ __device__ __forceinline__ void epilogue1_chunks(uint32_t lane_taddr, uint8_t* a
     }
 }
 
-// Epilogue 2 + layer 3 for hidden chunks [C0, C1): part += w3 . relu(acc), four independent chains.
+// Epilogue 2 + layer 3 for hidden chunks [C0, C1): part += (w3 / 2) . |acc|, four independent chains.  relu(h) is
+// (h + |h|) / 2: the linear half of the head, sum_n (w3_n / 2) h_n, is one more output unit of layer 2's GEMM (units 100,
+// 101: hi + lo of the combined row, see nimmt_policy_pack_weights), so the threads only add the |h| half — one FFMA with
+// an |x| operand per column instead of a max and an FFMA.
 template <int C0, int C1>
 __device__ __forceinline__ void epilogue2_chunks(uint32_t lane_taddr, const float* w3, float (&part)[4]) {
     uint32_t v[C1 - C0][16];
@@ -134,7 +138,7 @@ __device__ __forceinline__ void epilogue2_chunks(uint32_t lane_taddr, const floa
 #pragma unroll
     for (int c = C0; c < C1; ++c)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) part[i & 3] = fmaf(fmaxf(__uint_as_float(v[c - C0][i]), 0.0f), w3[c * 16 + i], part[i & 3]);
+        for (int i = 0; i < 16; ++i) part[i & 3] = fmaf(fabsf(__uint_as_float(v[c - C0][i])), w3[c * 16 + i], part[i & 3]);
 }
 
 // One 128-row tile through the three layers.  The 128 threads of a tile group call this together.
@@ -206,18 +210,20 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     phase ^= 1u;
     tc_fence_after_sync();
     pc.mark(5);
-    // epilogue 2 + layer 3: logit = w3 . relu(acc) + b3, fp32
+    // epilogue 2 + layer 3: logit = w3 . relu(acc) + b3 = (linear half from the GEMM) + (w3 / 2) . |acc| + b3, fp32
     float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     epilogue2_chunks<0, 4>(lane_taddr, w3, part);
     epilogue2_chunks<4, 6>(lane_taddr, w3, part);
+    float linear;
     {
-        uint32_t v[4];   // units 96..99: the last ones that exist
-        tmem_ld4(lane_taddr + 96, v);
+        uint32_t v[8];   // units 96..99: the last ones that exist; units 100, 101: the linear half of the head (hi, lo)
+        tmem_ld8(lane_taddr + 96, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) part[i] = fmaf(fmaxf(__uint_as_float(v[i]), 0.0f), w3[96 + i], part[i]);
+        for (int i = 0; i < 4; ++i) part[i] = fmaf(fabsf(__uint_as_float(v[i])), w3[96 + i], part[i]);
+        linear = __uint_as_float(v[4]) + __uint_as_float(v[5]);
     }
-    const float logit = b3 + ((part[0] + part[1]) + (part[2] + part[3]));
+    const float logit = (b3 + linear) + ((part[0] + part[1]) + (part[2] + part[3]));
     tc_fence_before_sync();      // ordered before the caller's next barrier / the next tile's MMA
     pc.mark(6);
     return logit;
