@@ -24,6 +24,7 @@ import torch
 from . import _native as N
 from . import policy as PL
 from . import rollouts as R
+from . import stats as S
 from . import train as T
 from .env import BatchedSechsNimmtEnv
 
@@ -92,6 +93,11 @@ class BatchedGameSession:
 
     def _stream(self):
         return torch.cuda.current_stream(self.env.device).cuda_stream
+
+    def statistics(self):
+        """Per-seat mean score, mean relative position and win rate over every game played so far (the reference
+        tournament's per-agent statistics, tournament.py:139-155, 240-256; stats.py)."""
+        return S.summary(torch.cat(self.results))
 
     def play_games(self):
         env, B, P = self.env, self.env.num_games, self.env.num_players

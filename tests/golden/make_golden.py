@@ -560,7 +560,26 @@ def make_policy_train(n_episodes=3):
     return out
 
 
+def make_position_stats(n=400):
+    """Tournament._compute_absolute_positions / _compute_relative_positions (tournament.py:240-256) and the winner rule
+    (np.argmax, :141) of the unmodified reference on random score vectors with many ties, P = 2..10."""
+    from ref_loader import load_tournament
+    T = load_tournament().Tournament
+    rng = np.random.RandomState(17)
+    cases = []
+    for _ in range(n):
+        P = int(rng.randint(2, 11))
+        scores = -rng.randint(0, 12, size=P).astype(np.int32)          # negative Hornochsen totals, ties are common
+        cases.append({"scores": scores.tolist(), "absolute": [float(x) for x in T._compute_absolute_positions(scores)],
+                      "relative": [float(x) for x in T._compute_relative_positions(scores)], "winner": int(np.argmax(scores))})
+    return cases
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-position-stats":
+        json.dump(make_position_stats(), open(os.path.join(HERE, "position_stats.json"), "w"), separators=(",", ":"))
+        print("position stats written")
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--only-policy-train":
         pt = make_policy_train()
         np.savez_compressed(os.path.join(HERE, "policy_train.npz"), **pt)
@@ -601,6 +620,7 @@ def main():
     pr = make_policy_rollouts()
     np.savez_compressed(os.path.join(HERE, "policy_rollouts.npz"), **pr)
     np.savez_compressed(os.path.join(HERE, "policy_train.npz"), **make_policy_train())
+    json.dump(make_position_stats(), open(os.path.join(HERE, "position_stats.json"), "w"), separators=(",", ":"))
 
 
 if __name__ == "__main__":

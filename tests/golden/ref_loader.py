@@ -62,3 +62,12 @@ def load_reference():
     ns.preprocessing = importlib.import_module("rl_6_nimmt.utils.preprocessing")
     ns.nets = importlib.import_module("rl_6_nimmt.utils.nets")
     return ns
+
+
+def load_tournament():
+    """rl_6_nimmt.tournament with an empty stand-in for the absent third-party `multi_elo` (tournament.py:5): only the
+    position statistics (static methods, tournament.py:240-256) are used; Elo is out of scope and unpinned."""
+    load_reference()
+    if "multi_elo" not in sys.modules:
+        sys.modules["multi_elo"] = types.ModuleType("multi_elo")
+    return importlib.import_module("rl_6_nimmt.tournament")

@@ -145,3 +145,16 @@ def test_reinforce_seat_samples_from_the_policy():
     assert totals.shape == (B, 3) and int(env.illegal.sum()) == 0
     greedy = BatchedGameSession([ReinforceSeat(net, greedy=True), RandomSeat()], 256, seed=1).play_games()
     assert greedy.shape == (256, 2)
+
+
+def test_session_statistics_on_device():
+    """BatchedGameSession.statistics(): the tournament's per-agent numbers (mean score, relative position, win rate) over
+    all games so far; an MCS seat must beat two random seats on every one of them."""
+    sess = BatchedGameSession([MCSSeat(mc_max=100), RandomSeat(), RandomSeat()], 4096, seed=3)
+    sess.play_games()
+    sess.play_games()
+    st = {k: v.cpu().numpy() for k, v in sess.statistics().items()}
+    assert st["mean_score"].shape == (3,) and abs(st["win_rate"].sum() - 1.0) < 1e-9
+    assert st["mean_score"][0] > st["mean_score"][1:].max() + 2.0
+    assert st["mean_relative_position"][0] > 0.6 > st["mean_relative_position"][1:].max()
+    assert st["win_rate"][0] > 0.45
