@@ -58,7 +58,10 @@ class PolicySeat(MCSSeat):
 
 class ReinforceSeat:
     """A model-free policy-gradient opponent at the table: one k_policy_probs launch per turn
-    and a categorical draw per game; ``greedy=True`` plays the most probable card instead."""
+    and a categorical draw per game; ``greedy=True`` plays the most probable card instead.  ``net`` is anything with
+    the parameter names of the reference's ``MultiHeadedMLP(48, (100, 100), (1, ...))``: BatchedReinforceAgent's
+    ``actor`` (agents/policy.py:134) or ACER's ``actor_critic`` (agents/actor_critic.py:44-46; its first head is the
+    policy logit, the value head is ignored)."""
 
     def __init__(self, net, greedy=False):
         self.net, self.weights, self.greedy = net, PL.pack_weights(net), bool(greedy)

@@ -69,3 +69,15 @@ def test_batched_step_is_the_mean_of_the_episode_losses():
     assert abs(float(loss) - np.mean(per_episode)) < 1e-5
     for i, p in enumerate(net.parameters()):
         torch.testing.assert_close(p.grad, sum(g[i] for g in grads) / 3, rtol=1e-4, atol=1e-6)
+
+
+def test_two_headed_actor_critic_packs_like_its_policy_head():
+    """ACER's net is MultiHeadedMLP(48, (100, 100), head_sizes=(1, 1)) (agents/actor_critic.py:44-46): its first head is the
+    policy logit, so a ReinforceSeat can seat it — pack_weights reads head_nets.0.0 and ignores the value head."""
+    from torch import nn
+    torch.manual_seed(4)
+    one = PL.PolicyNet()
+    two = PL.PolicyNet()
+    two.head_nets.append(nn.Sequential(nn.Linear(100, 1)))          # the critic head
+    two.load_state_dict({**one.state_dict(), **{k: v for k, v in two.state_dict().items() if k.startswith("head_nets.1.")}})
+    assert torch.equal(PL.pack_weights(one, device="cpu"), PL.pack_weights(two, device="cpu"))
