@@ -10,6 +10,8 @@ small spec objects instead of per-game Python agents:
     PolicySeat(net, mc_max=100, puct=True)         PUCTAgent / PolicyMCSAgent (agents/mcts.py:191-323)
     ReinforceSeat(net)                             BatchedReinforceAgent.forward (agents/policy.py:137-156), inference:
                                                    the same 48-100-100-1 net, a card sampled from its softmax, no search
+    MaskedPolicySeat(net)                          MaskedReinforceAgent.forward (agents/policy.py:45-60): a 47 -> 104 net,
+                                                   softmax over the cards in hand (greedy=True: a DQN's argmax)
 
 Everything — card memory, root construction, rollouts, the decision rule, the env step — runs in
 kernels; the host only sequences launches.  ``PolicySeat(..., learn=True)`` closes the Alpha0.5 self-play loop
@@ -67,6 +69,15 @@ class ReinforceSeat:
         self.net, self.weights, self.greedy = net, PL.pack_weights(net), bool(greedy)
 
 
+class MaskedPolicySeat:
+    """A state-only net with one output per card at the table (MaskedReinforceAgent.forward, agents/policy.py:45-60; a DQN's
+    Q-values with ``greedy=True``): normalise the observation, one forward pass of ``net`` for all games (PyTorch on the
+    device: plain library GEMMs), restrict to the cards in hand, softmax, sample or take the argmax."""
+
+    def __init__(self, net, greedy=False):
+        self.net, self.greedy = net, bool(greedy)
+
+
 class BatchedGameSession:
     def __init__(self, seats, num_games, device=None, seed=0):
         self.seats = list(seats)
@@ -116,11 +127,15 @@ class BatchedGameSession:
             for p, seat in enumerate(self.seats):
                 if isinstance(seat, RandomSeat):
                     continue
-                if isinstance(seat, ReinforceSeat):
+                if isinstance(seat, (ReinforceSeat, MaskedPolicySeat)):
                     if obs8 is None:
                         obs8 = env.observe(dtype=torch.int8)
                     mine = obs8[:, p].contiguous()
-                    probs = PL.policy_probs(mine, seat.weights)                    # [B,10] by hand slot, 0 for empty slots
+                    if isinstance(seat, MaskedPolicySeat):
+                        with torch.no_grad():
+                            probs = PL.masked_card_probs(seat.net.to(env.device), mine)
+                    else:
+                        probs = PL.policy_probs(mine, seat.weights)                # [B,10] by hand slot, 0 for empty slots
                     slot = probs.argmax(dim=1, keepdim=True) if seat.greedy else torch.multinomial(probs, 1, generator=self._generator)
                     actions[:, p] = mine[:, :10].gather(1, slot).squeeze(1).to(torch.uint8)
                     continue

@@ -43,6 +43,29 @@ def normalize_rows(rows):
     return rows * scale + shift
 
 
+def normalize_states(obs):
+    """SechsNimmtStateNormalization(action=False).forward (utils/preprocessing.py:12-57): the 47-vector without a
+    candidate card in front, as the state-only nets consume it (MaskedReinforceAgent, agents/policy.py:38)."""
+    scale = torch.empty(47, dtype=obs.dtype, device=obs.device)
+    shift = torch.empty(47, dtype=obs.dtype, device=obs.device)
+    for a, b, lo, hi in _SEGMENTS[1:]:
+        scale[a - 1:b - 1] = 2.0 / (hi - lo)
+        shift[a - 1:b - 1] = -1.0 - 2.0 * lo / (hi - lo)
+    return obs * scale + shift
+
+
+def masked_card_probs(net, obs):
+    """MaskedReinforceAgent.forward up to the sampling (agents/policy.py:45-50) for a batch: obs [D,47] (any dtype) ->
+    probabilities float32 [D,10] over the hand slots (0 for empty slots).  ``net`` maps normalised states [D,47] to a
+    list whose first entry holds one logit per card [D,104] (``MultiHeadedMLP(47, hidden, (104,))``); plain library GEMMs."""
+    obs = obs.to(torch.float32)
+    (logits,) = net(normalize_states(obs))[:1]
+    hand = obs[:, :10].to(torch.int64)
+    legal = hand >= 0
+    picked = logits.gather(1, hand.clamp(min=0)).masked_fill(~legal, float("-inf"))
+    return torch.softmax(picked, dim=1)
+
+
 def torch_policy(net, state, legal_actions):
     """PolicyMCSAgent._compute_policy (agents/mcts.py:219-228) with autograd: probabilities over the legal cards."""
     state = torch.as_tensor(state, dtype=torch.float32).reshape(-1)

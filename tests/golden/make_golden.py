@@ -575,7 +575,47 @@ def make_position_stats(n=400):
     return cases
 
 
+def make_masked_policy(n_games=3):
+    """MaskedReinforceAgent.forward (agents/policy.py:45-60): state -> SechsNimmtStateNormalization(action=False) ->
+    MultiHeadedMLP(47, (100, 100), (104,)) -> logits of the legal cards -> softmax.  Weights, states, legal cards, the
+    normalised states and the probabilities over the legal cards for every seat and turn of a few random games."""
+    import torch
+    from ref_loader import load_policy_agents
+    pol = load_policy_agents()
+    torch.manual_seed(9)
+    agent = pol.MaskedReinforceAgent()
+    out = {"w_" + k.replace(".", "_"): v.detach().numpy().copy() for k, v in agent.state_dict().items()}
+    np.random.seed(41)
+    env = Env(4, verbose=False)
+    states_all, norm_all, probs_all, legal_all = [], [], [], []
+    for g in range(n_games):
+        states, legal = env.reset()
+        done = False
+        while not done:
+            for p in range(4):
+                st = torch.tensor(states[p]).to(torch.float)
+                la = torch.tensor(list(map(int, legal[p])))
+                norm = agent.preprocessor(st)
+                (logits,) = agent.actor(norm)
+                probs = agent.softmax(logits[la])
+                row = np.zeros(10, np.float32)
+                row[: len(la)] = probs.detach().numpy()
+                states_all.append(np.array(states[p], np.int8)); norm_all.append(norm.detach().numpy()); probs_all.append(row)
+                legal_all.append(len(la))
+            (states, legal), _, done, _ = env.step([int(np.random.choice(l)) for l in legal])
+    out["states"] = np.array(states_all, np.int8)
+    out["norm"] = np.array(norm_all, np.float32)
+    out["probs"] = np.array(probs_all, np.float32)
+    out["n_legal"] = np.array(legal_all, np.int32)
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-masked-policy":
+        mp = make_masked_policy()
+        np.savez_compressed(os.path.join(HERE, "masked_policy.npz"), **mp)
+        print("masked policy:", mp["states"].shape, mp["probs"][0])
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--only-position-stats":
         json.dump(make_position_stats(), open(os.path.join(HERE, "position_stats.json"), "w"), separators=(",", ":"))
         print("position stats written")

@@ -71,3 +71,16 @@ def load_tournament():
     if "multi_elo" not in sys.modules:
         sys.modules["multi_elo"] = types.ModuleType("multi_elo")
     return importlib.import_module("rl_6_nimmt.tournament")
+
+
+def load_policy_agents():
+    """rl_6_nimmt.agents.policy (MaskedReinforceAgent, BatchedReinforceAgent) with an empty stand-in for matplotlib, which
+    utils/various.py:4 imports for plotting only."""
+    load_reference()
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.lines"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].__path__ = []
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib.lines"].Line2D = object
+    return importlib.import_module("rl_6_nimmt.agents.policy")

@@ -7,7 +7,7 @@ import rl_6_nimmt_b200  # noqa: F401
 from rl_6_nimmt_b200 import _native as N
 from rl_6_nimmt_b200 import rollouts as R
 from rl_6_nimmt_b200.agents import MCSAgent
-from rl_6_nimmt_b200.play import BatchedGameSession, MCSSeat, PolicySeat, RandomSeat, ReinforceSeat
+from rl_6_nimmt_b200.play import BatchedGameSession, MaskedPolicySeat, MCSSeat, PolicySeat, RandomSeat, ReinforceSeat
 from rl_6_nimmt_b200 import policy as PL
 
 pytestmark = pytest.mark.gpu
@@ -158,3 +158,26 @@ def test_session_statistics_on_device():
     assert st["mean_score"][0] > st["mean_score"][1:].max() + 2.0
     assert st["mean_relative_position"][0] > 0.6 > st["mean_relative_position"][1:].max()
     assert st["win_rate"][0] > 0.45
+
+
+def test_masked_policy_seat_plays_legal_cards():
+    """A 47 -> 104 state-only net (MaskedReinforceAgent / DQN shape) at the table, sampled and greedy: every card played is
+    in the player's hand and the session finishes."""
+    from torch import nn
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.latent_net = nn.Sequential(nn.Linear(47, 100), nn.ReLU(), nn.Linear(100, 100), nn.ReLU())
+            self.head_nets = nn.ModuleList([nn.Sequential(nn.Linear(100, 104))])
+
+        def forward(self, x):
+            h = self.latent_net(x)
+            return [head(h) for head in self.head_nets]
+
+    torch.manual_seed(2)
+    net = Net()
+    for greedy in (False, True):
+        sess = BatchedGameSession([MaskedPolicySeat(net, greedy=greedy), RandomSeat(), MCSSeat(mc_max=20)], 2048, seed=6)
+        totals = sess.play_games()
+        assert totals.shape == (2048, 3) and int(sess.env.illegal.sum()) == 0 and bool(sess.env.done.all())

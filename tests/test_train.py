@@ -81,3 +81,30 @@ def test_two_headed_actor_critic_packs_like_its_policy_head():
     two.head_nets.append(nn.Sequential(nn.Linear(100, 1)))          # the critic head
     two.load_state_dict({**one.state_dict(), **{k: v for k, v in two.state_dict().items() if k.startswith("head_nets.1.")}})
     assert torch.equal(PL.pack_weights(one, device="cpu"), PL.pack_weights(two, device="cpu"))
+
+
+def test_masked_policy_probs_match_the_reference():
+    """policy.masked_card_probs against MaskedReinforceAgent.forward of the unmodified reference (normalisation without the
+    action feature, 47 -> 100 -> 100 -> 104 net, softmax over the legal cards): tests/golden/masked_policy.npz."""
+    from torch import nn
+    z = np.load(os.path.join(GOLDEN, "masked_policy.npz"))
+
+    class Net(nn.Module):                                 # the reference's MultiHeadedMLP(47, (100, 100), (104,)) parameter tree
+        def __init__(self):
+            super().__init__()
+            self.latent_net = nn.Sequential(nn.Linear(47, 100), nn.ReLU(), nn.Linear(100, 100), nn.ReLU())
+            self.head_nets = nn.ModuleList([nn.Sequential(nn.Linear(100, 104))])
+
+        def forward(self, x):
+            h = self.latent_net(x)
+            return [head(h) for head in self.head_nets]
+
+    net = Net()
+    net.load_state_dict({k[len("w_actor_"):].replace("latent_net_0_", "latent_net.0.").replace("latent_net_2_", "latent_net.2.")
+                         .replace("head_nets_0_0_", "head_nets.0.0."): torch.from_numpy(z[k]) for k in z.files if k.startswith("w_actor_")})
+    obs = torch.from_numpy(z["states"])
+    np.testing.assert_allclose(PL.normalize_states(obs.to(torch.float32)).numpy(), z["norm"], rtol=1e-6, atol=1e-6)
+    with torch.no_grad():
+        probs = PL.masked_card_probs(net, obs).numpy()
+    np.testing.assert_allclose(probs, z["probs"], rtol=1e-4, atol=1e-6)
+    assert ((probs > 0).sum(axis=1) == z["n_legal"]).all()
