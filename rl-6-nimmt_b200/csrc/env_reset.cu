@@ -9,16 +9,18 @@ thread_local char g_last_error[256] = "";
 // ------------------------------------------------------------------------------------------
 // k_deal — SechsNimmtEnv.reset/_deal (env.py:43-51, 99-112).  Write-only: (12 P + 24) B/game.
 // ------------------------------------------------------------------------------------------
+constexpr int kDealThreads = 64;   // 104 words x 64 threads = 26 KB of interleaved decks per block
+
 template <int P>
-__global__ void __launch_bounds__(kStepThreads) k_deal(StateView s, uint64_t seed, uint64_t game0) {
+__global__ void __launch_bounds__(kDealThreads) k_deal(StateView s, uint64_t seed, uint64_t game0) {
     __shared__ uint8_t values[128];
-    __shared__ __align__(4) uint8_t decks[kStepThreads * kDeckStride];
+    __shared__ uint32_t decks[kCards * kDealThreads];
     stage_card_values(values);
     __syncthreads();
-    const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
+    const int64_t g = (int64_t)blockIdx.x * kDealThreads + threadIdx.x;
     if (g >= s.B) return;
     GameRec<P> gm;
-    deal_game<P>(gm, seed, game0 + (uint64_t)g, values, decks + threadIdx.x * kDeckStride);
+    deal_game<P>(gm, seed, game0 + (uint64_t)g, values, decks + threadIdx.x, kDealThreads);
     store_game<P>(s, g, gm);
 }
 
@@ -142,7 +144,7 @@ int nimmt_deal(void* state, int64_t B, int num_players, uint64_t seed, uint64_t 
     if (int rc = check_common(state, B, num_players)) return rc;
     if (B == 0) return NIMMT_OK;
     StateView s(state, B, num_players);
-    NIMMT_DISPATCH_P(num_players, k_deal<P><<<blocks_for(B, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(s, seed, game0));
+    NIMMT_DISPATCH_P(num_players, k_deal<P><<<blocks_for(B, kDealThreads), kDealThreads, 0, (cudaStream_t)stream>>>(s, seed, game0));
     return check_launch();
 }
 

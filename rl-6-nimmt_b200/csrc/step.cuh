@@ -111,7 +111,10 @@ NIMMT_HD bool game_done(const GameRec<P>& g) { return rec_empty(g.hand[0]); }
 // 104-card deck, 10 P + 4 draws.  Draw i < 10 P goes to hand i / 10 (the reference's
 // perm[10p .. 10p+9]), draw 10 P + r opens row r (the reference's perm[103 - r]): a prefix plus
 // four more entries of a uniform permutation, which is all the reference's shuffle provides.
-// `deck` is 104 bytes of scratch private to this game (a slice of shared memory on the device,
+// `deck` is the game's private 104-entry scratch, one 32-bit word per card at a stride of `deck_stride` words: on the
+// device the block's decks are interleaved (entry j of thread t at word j * threads + t), so the 32 games of a warp hit
+// 32 different banks whatever positions they draw — byte decks at a per-thread stride cost ~3.5 wavefronts per access
+// (a slice of shared memory on the device,
 // kDeckStride bytes apart so that equal indices of different threads fall in different banks).
 constexpr int kDeckStride = 116;  // 29 words: odd word stride
 
@@ -133,10 +136,10 @@ NIMMT_HD void set_dealt_hand(GameRec<P>& g, int p, int (&cards)[kHand]) {
 }
 
 template <int P, class G>
-NIMMT_HD void deal_game(G& g, uint64_t seed, uint64_t game_id, const uint8_t* values, uint8_t* deck) {
+NIMMT_HD void deal_game(G& g, uint64_t seed, uint64_t game_id, const uint8_t* values, uint32_t* deck, int deck_stride) {
     Philox rng(seed, game_id, /*stream=*/0x6e696d74u, 0);
 #pragma unroll
-    for (int i = 0; i < kCards / 4; ++i) reinterpret_cast<uint32_t*>(deck)[i] = 0x03020100u + 0x04040404u * (uint32_t)i;
+    for (int i = 0; i < kCards; ++i) deck[i * deck_stride] = (uint32_t)i;
     // two draws per 32-bit word (below_keep): one Philox4x32-7 call serves eight cards
     uint4 r = make_uint4(0, 0, 0, 0);
     uint32_t spare = 0;
@@ -150,8 +153,8 @@ NIMMT_HD void deal_game(G& g, uint64_t seed, uint64_t game_id, const uint8_t* va
             off = below(spare, (uint32_t)(kCards - i));
         }
         const uint32_t j = (uint32_t)i + off;
-        const uint32_t card = deck[j];
-        deck[j] = deck[i];   // position i is never read again, so only half of the swap is needed
+        const uint32_t card = deck[j * deck_stride];
+        deck[j * deck_stride] = deck[i * deck_stride];   // position i is never read again, so only half of the swap is needed
         return card;
     };
 #pragma unroll

@@ -96,8 +96,8 @@ static void deal(int n, uint64_t seed, uint64_t game0, int8_t* hands, int8_t* bo
     int16_t sc[P];
     for (int gi = 0; gi < n; ++gi) {
         G g;
-        alignas(4) uint8_t deck[kDeckStride];
-        deal_game<P>(g, seed, game0 + gi, h_card_value, deck);
+        uint32_t deck[kCards];
+        deal_game<P>(g, seed, game0 + gi, h_card_value, deck, 1);
         unpack_to_arrays<P>(g, hands + (size_t)gi * P * 10, boards + (size_t)gi * 24, sc);
     }
 }
