@@ -117,6 +117,13 @@ def _bf16_hi_lo(b):
     return hi + _bf16(np.asarray(b, np.float32) - hi)
 
 
+def _bf16_three_terms(b):
+    b = np.asarray(b, np.float32)
+    hi = _bf16(b)
+    mid = _bf16(b - hi)
+    return hi.astype(np.float64) + mid + _bf16(b - hi - mid)
+
+
 def policy_logits_bf16(rows, w):
     w1f, b1f = fold_normalization(w)
     x = _bf16(rows)                      # raw features are small integers: exact
@@ -125,10 +132,10 @@ def policy_logits_bf16(rows, w):
     w2b, b2b = _bf16(w["w2"]), _bf16_hi_lo(w["b2"])
     h2 = (a2 @ w2b.T + b2b).astype(np.float32)
     # relu(h) = (h + |h|) / 2: the linear half of the head rides in the GEMM as one more output unit whose weights are the
-    # combined row sum_n (w3_n / 2) [W2 | b2]_n, carried as hi + lo bf16 terms; the threads add the |h| half in fp32
+    # combined row sum_n (w3_n / 2) [W2 | b2]_n, carried as three bf16 terms; the threads add the |h| half in fp32
     w3h = (0.5 * w["w3"].reshape(-1).astype(np.float64))
-    row = _bf16_hi_lo((w3h @ w2b.astype(np.float64)).astype(np.float32))
-    bias = _bf16_hi_lo(np.array([(w3h * b2b.astype(np.float64)).sum()], np.float32))[0]
+    row = _bf16_three_terms((w3h @ w2b.astype(np.float64)).astype(np.float32))
+    bias = _bf16_three_terms(np.array([(w3h * b2b.astype(np.float64)).sum()], np.float32))[0]
     linear = (a2 @ row + bias).astype(np.float32)
     return (linear + np.abs(h2) @ w3h.astype(np.float32) + np.float32(w["b3"].reshape(-1)[0])).astype(np.float32)
 

@@ -158,16 +158,19 @@ int nimmt_policy_pack_weights(const float* w1, const float* b1, const float* w2,
         put2(n, kOneUnit + 1, lo);
         w3p[n] = 0.5f * w3[n];                 // the |h| half of relu(h) = (h + |h|) / 2
     }
-    // the linear half, sum_n (w3_n / 2) h_n, as output units 100 (hi) and 101 (lo) of layer 2: the combined row is formed
-    // from the bf16 weights the tensor core really multiplies by, bias columns included
+    // the linear half, sum_n (w3_n / 2) h_n, as output units 100, 101, 102 of layer 2 (three bf16 terms: the two halves of
+    // the head cancel wherever units are inactive, so this row is carried to ~24 bits): the combined row is formed from
+    // the bf16 weights the tensor core really multiplies by, bias columns included
     for (int k = 0; k < kOneUnit + 2; ++k) {
         double acc = 0.0;
         for (int n = 0; n < kHid; ++n)
             acc += 0.5 * (double)w3[n] * (double)bf16_to_float(*reinterpret_cast<const uint16_t*>(blob + kOffW2 + canon_off(n, k, kHidChunks)));
-        uint16_t hi, lo;
-        split((float)acc, hi, lo);
-        put2(kOneUnit, k, hi);
-        put2(kOneUnit + 1, k, lo);
+        float rest = (float)acc;
+        for (int t = 0; t < 3; ++t) {
+            const uint16_t term = float_to_bf16_rne(rest);
+            put2(kOneUnit + t, k, term);
+            rest -= bf16_to_float(term);
+        }
     }
     put1(kOneUnit, kBiasCol, 0x3F80);       // units 100, 101 of layer 1: relu(1 * 1) = 1, the inputs that carry b2
     put1(kOneUnit + 1, kBiasCol, 0x3F80);

@@ -126,9 +126,9 @@ __device__ __forceinline__ void epilogue1_chunks(uint32_t lane_taddr, uint8_t* a
 }
 
 // Epilogue 2 + layer 3 for hidden chunks [C0, C1): part += (w3 / 2) . |acc|, four independent chains.  relu(h) is
-// (h + |h|) / 2: the linear half of the head, sum_n (w3_n / 2) h_n, is one more output unit of layer 2's GEMM (units 100,
-// 101: hi + lo of the combined row, see nimmt_policy_pack_weights), so the threads only add the |h| half — one FFMA with
-// an |x| operand per column instead of a max and an FFMA.
+// (h + |h|) / 2: the linear half of the head, sum_n (w3_n / 2) h_n, is one more output unit of layer 2's GEMM (units
+// 100..102: three bf16 terms of the combined row, see nimmt_policy_pack_weights), so the threads only add the |h| half —
+// one FFMA with an |x| operand per column instead of a max and an FFMA.
 template <int C0, int C1>
 __device__ __forceinline__ void epilogue2_chunks(uint32_t lane_taddr, const float* w3, float (&part)[4]) {
     uint32_t v[C1 - C0][16];
@@ -216,12 +216,12 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     epilogue2_chunks<4, 6>(lane_taddr, w3, part);
     float linear;
     {
-        uint32_t v[8];   // units 96..99: the last ones that exist; units 100, 101: the linear half of the head (hi, lo)
+        uint32_t v[8];   // units 96..99: the last ones that exist; units 100..102: the linear half of the head (three terms)
         tmem_ld8(lane_taddr + 96, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) part[i] = fmaf(fabsf(__uint_as_float(v[i])), w3[96 + i], part[i]);
-        linear = __uint_as_float(v[4]) + __uint_as_float(v[5]);
+        linear = (__uint_as_float(v[6]) + __uint_as_float(v[5])) + __uint_as_float(v[4]);
     }
     const float logit = (b3 + linear) + ((part[0] + part[1]) + (part[2] + part[3]));
     tc_fence_before_sync();      // ordered before the caller's next barrier / the next tile's MMA
