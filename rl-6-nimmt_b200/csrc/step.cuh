@@ -113,10 +113,7 @@ NIMMT_HD bool game_done(const GameRec<P>& g) { return rec_empty(g.hand[0]); }
 // four more entries of a uniform permutation, which is all the reference's shuffle provides.
 // `deck` is the game's private 104-entry scratch, one 32-bit word per card at a stride of `deck_stride` words: on the
 // device the block's decks are interleaved (entry j of thread t at word j * threads + t), so the 32 games of a warp hit
-// 32 different banks whatever positions they draw — byte decks at a per-thread stride cost ~3.5 wavefronts per access
-// (a slice of shared memory on the device,
-// kDeckStride bytes apart so that equal indices of different threads fall in different banks).
-constexpr int kDeckStride = 116;  // 29 words: odd word stride
+// 32 different banks whatever positions they draw (byte decks at a per-thread stride cost ~3.5 wavefronts per access).
 
 // The ten cards dealt to player p (any order) become its hand.
 template <int P>
