@@ -150,7 +150,8 @@ static int mcs(const nimmt_root& root, int64_t R, uint64_t seed, int rank, int w
     for (int a = 0; a < n; ++a) {
         for (int64_t j = rank; j < R; j += world) {
             const uint64_t id = ((uint64_t)a << 40) | (uint64_t)j;  // root index d = 0
-            const int out = rollout<P>(rr, a, h_card_value, deck, seed, id);
+            alignas(16) int kw[4], ku[4];
+            const int out = rollout<P>(rr, a, h_card_value, deck, kw, ku, seed, id);
             stats[a * 3 + 0] += out; stats[a * 3 + 1] += (int64_t)out * out; stats[a * 3 + 2] += 1;
         }
     }
