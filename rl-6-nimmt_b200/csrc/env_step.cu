@@ -105,7 +105,7 @@ __device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* re
 
 // One game, in place in the tile buffer.  `lane` selects the game.
 template <int P>
-__device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8_t* values) {
+__device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8_t* values, int* keys_w, int* keys_u) {
     using L = TileLayout<P>;
     const uint2* cards0 = reinterpret_cast<const uint2*>(buf) + lane;             // + p * kTileGames
     uint32_t* meta0 = reinterpret_cast<uint32_t*>(buf + L::kMeta) + lane;         // + p * kTileGames
@@ -140,15 +140,20 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
 
     bool done = (meta0[0] & kSlotBits) == kSlotBits;   // an illegal step leaves the game as it was
     if (legal) {
-        // comparison keys of the four rows (game.cuh::RowKeys) from the record
-        RowKeys rk;
-        const uint32_t metas = *reinterpret_cast<const uint32_t*>(rec + 20);
+        // comparison keys of the four rows (game.cuh::RowKeys) from the record, kept in this lane's indexable scratch
+        // (game.cuh::place_indexed)
+        {
+            int w[kRows], u[kRows];
+            const uint32_t metas = *reinterpret_cast<const uint32_t*>(rec + 20);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-            const uint32_t m = (metas >> (8 * r)) & 0xFFu;
-            const uint32_t top = rec[4 * ((m & 7u) - 1u) + r];
-            rk.w[r] = (int)((top << 10) | (m << 2) | (uint32_t)r);
-            rk.u[r] = (int)(((m >> 3) << 2) | (uint32_t)r);
+            for (int r = 0; r < kRows; ++r) {
+                const uint32_t m = (metas >> (8 * r)) & 0xFFu;
+                const uint32_t top = rec[4 * ((m & 7u) - 1u) + r];
+                w[r] = (int)((top << 10) | (m << 2) | (uint32_t)r);
+                u[r] = (int)(((m >> 3) << 2) | (uint32_t)r);
+            }
+            *reinterpret_cast<int4*>(keys_w) = make_int4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<int4*>(keys_u) = make_int4(u[0], u[1], u[2], u[3]);
         }
 
         int keys[P];
@@ -161,7 +166,7 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
             const int card = keys[i] >> 4, player = keys[i] & 15;
             int row;
             uint32_t keep_len;
-            const int pen = rk.place(card, values[card], row, keep_len);   // env.py:126-134
+            const int pen = place_indexed(keys_w, keys_u, card, values[card], row, keep_len);   // env.py:126-134
             rec[4 * keep_len + row] = (uint8_t)card;   // the one byte of the record a placement changes
             if (pen != 0) {                            // a take (rare): env.py:167-169
 #pragma unroll
@@ -172,9 +177,11 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
 #pragma unroll
         for (int p = 0; p < P; ++p) meta0[p * kTileGames] = meta[p];   // env.py:131: the played slots are empty now
 
+        const int4 fw = *reinterpret_cast<const int4*>(keys_w);
+        const int w_final[kRows] = {fw.x, fw.y, fw.z, fw.w};
         uint32_t new_metas = 0;
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) new_metas |= (((uint32_t)rk.w[r] >> 2) & 0xFFu) << (8 * r);
+        for (int r = 0; r < kRows; ++r) new_metas |= (((uint32_t)w_final[r] >> 2) & 0xFFu) << (8 * r);
         *reinterpret_cast<uint32_t*>(rec + 20) = new_metas;
         done = (meta[0] & kSlotBits) == kSlotBits;     // env.py:246-249
     }
@@ -190,6 +197,7 @@ k_step_smem(StateView s, const uint8_t* __restrict__ actions, int8_t* __restrict
     extern __shared__ __align__(128) uint8_t tile_smem[];   // kSmemWarps x 2 x L::kStride
     __shared__ uint64_t full[kSmemWarps][2];
     __shared__ uint8_t values[128];
+    __shared__ int4 keys_w[kSmemWarps * 32], keys_u[kSmemWarps * 32];   // each lane's row keys, indexable
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* bufs = tile_smem + warp * 2 * L::kStride;
@@ -210,7 +218,7 @@ k_step_smem(StateView s, const uint8_t* __restrict__ actions, int8_t* __restrict
         const int b = it & 1;
         uint8_t* buf = bufs + b * L::kStride;
         mbar_wait(&full[warp][b], (uint32_t)(it >> 1) & 1u);
-        step_in_smem<P>(buf, lane, values);
+        step_in_smem<P>(buf, lane, values, reinterpret_cast<int*>(&keys_w[threadIdx.x]), reinterpret_cast<int*>(&keys_u[threadIdx.x]));
         fence_async_smem();   // make this lane's shared-memory writes visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
