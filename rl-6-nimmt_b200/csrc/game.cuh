@@ -283,8 +283,19 @@ struct RowKeys {
 // 16-byte aligned: shared memory on the device).  The four rows are read with two 128-bit loads and the one row that
 // changes is written with two 32-bit stores, instead of the eight predicated selects (and four compares) that keeping the
 // rows in registers costs — the kernels that call this are bound by the ALU pipe, not by the load/store pipe.
+// STRIDE = 1: the four words of a group are contiguous (one 128-bit load each).  STRIDE = n: row r of this thread sits
+// at word r * n — the threads of a block interleave their groups, so that every load and, above all, the store to the
+// data-dependent row r is free of bank conflicts.
+template <int STRIDE = 1>
 NIMMT_HD int place_indexed(int* w, int* u, int card, int value, int& row, uint32_t& keep_len) {
-    const int4 W = *reinterpret_cast<const int4*>(w), U = *reinterpret_cast<const int4*>(u);
+    int4 W, U;
+    if constexpr (STRIDE == 1) {
+        W = *reinterpret_cast<const int4*>(w);
+        U = *reinterpret_cast<const int4*>(u);
+    } else {
+        W = make_int4(w[0], w[STRIDE], w[2 * STRIDE], w[3 * STRIDE]);
+        U = make_int4(u[0], u[STRIDE], u[2 * STRIDE], u[3 * STRIDE]);
+    }
     const int ck = card << 10;
     const uint32_t d0 = (uint32_t)(ck - W.x), d1 = (uint32_t)(ck - W.y), d2 = (uint32_t)(ck - W.z), d3 = (uint32_t)(ck - W.w);
     const uint32_t dmin = umin32(umin32(d0, d1), umin32(d2, d3));
@@ -297,8 +308,8 @@ NIMMT_HD int place_indexed(int* w, int* u, int card, int value, int& row, uint32
     const bool take = under || len == 5u;
     keep_len = take ? 0u : len;
     const uint32_t new_sum = (take ? 0u : sum) + (uint32_t)value;
-    w[r] = ck | (int)((new_sum << 5) | ((keep_len + 1u) << 2)) | r;
-    u[r] = (int)(new_sum << 2) | r;
+    w[r * STRIDE] = ck | (int)((new_sum << 5) | ((keep_len + 1u) << 2)) | r;
+    u[r * STRIDE] = (int)(new_sum << 2) | r;
     row = r;
     return take ? (int)sum : 0;
 }

@@ -28,7 +28,7 @@ k_mcs_rollouts(const nimmt_root* __restrict__ roots, int64_t local_rollouts, int
     __shared__ RolloutRoot rr;
     __shared__ int root_ok;
     __shared__ __align__(4) uint8_t decks[kMcsThreads * kRolloutDeckStride];
-    __shared__ int4 keys_w[kMcsThreads], keys_u[kMcsThreads];   // each thread's row keys: indexable, 16 B per thread per array
+    __shared__ int keys_w[kRows * kMcsThreads], keys_u[kRows * kMcsThreads];   // row r of thread t at [r * threads + t]: conflict-free
     // cooperative version of make_rollout_root (rollout.cuh): thread c places card c at its rank in the
     // ascending pool / own lists, so building the 116-byte record costs ~20 instructions per thread
     {
@@ -69,7 +69,7 @@ k_mcs_rollouts(const nimmt_root* __restrict__ roots, int64_t local_rollouts, int
         if (i < local_rollouts) {
             const uint64_t j = (uint64_t)rank + (uint64_t)i * (uint64_t)world;
             const uint64_t id = ((uint64_t)d << 44) | ((uint64_t)a << 40) | j;
-            const int out = rollout<P>(rr, a, values, deck, reinterpret_cast<int*>(&keys_w[threadIdx.x]), reinterpret_cast<int*>(&keys_u[threadIdx.x]), seed, id);
+            const int out = rollout<P, kMcsThreads>(rr, a, values, deck, keys_w + threadIdx.x, keys_u + threadIdx.x, seed, id);
             s += out; ss += (long long)out * out; cnt += 1;
         }
     }

@@ -109,15 +109,15 @@ NIMMT_HD void draw_opponents(TurnWords<P>& words, uint8_t* deck, uint32_t& drawn
 // P-1 cards per turn from the pool prefix, player 0's card by swap-remove from its own list — a few
 // shared-memory byte accesses per draw instead of a popcount search through a 104-bit mask.
 // Returns the outcome (sum of player 0's rewards, <= 0).  Depends on (seed, rollout_id) only.
-// `keys` is 8 ints of scratch private to the caller, 16-byte aligned (row keys w[4], u[4]: game.cuh::place_indexed).
-template <int P>
+// keys_w / keys_u: the caller's private row keys (game.cuh::place_indexed), row r at word r * KEY_STRIDE.
+template <int P, int KEY_STRIDE = 1>
 NIMMT_HD int rollout(const RolloutRoot& rr, int first_index, const uint8_t* values, uint8_t* deck, int* keys_w, int* keys_u, uint64_t seed,
                      uint64_t rollout_id) {
 #pragma unroll
     for (int w = 0; w < kRolloutDeckStride / 4; ++w) reinterpret_cast<uint32_t*>(deck)[w] = reinterpret_cast<const uint32_t*>(rr.deck)[w];
     Philox rng(seed, rollout_id, /*stream=*/0x6d637300u, 0);
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) { keys_w[r] = rr.board.w[r]; keys_u[r] = rr.board.u[r]; }
+    for (int r = 0; r < kRows; ++r) { keys_w[r * KEY_STRIDE] = rr.board.w[r]; keys_u[r * KEY_STRIDE] = rr.board.u[r]; }
     int n_own = rr.n_own;
     uint32_t drawn = 0;
     const uint32_t n_pool = (uint32_t)rr.n_pool;
@@ -143,7 +143,7 @@ NIMMT_HD int rollout(const RolloutRoot& rr, int first_index, const uint8_t* valu
             const int card = keys[i] >> 4;
             int row;
             uint32_t keep_len;
-            const int pen = place_indexed(keys_w, keys_u, card, values[card], row, keep_len);
+            const int pen = place_indexed<KEY_STRIDE>(keys_w, keys_u, card, values[card], row, keep_len);
             outcome -= (keys[i] & 15) == 0 ? pen : 0;   // mcts.py:150: player 0's rewards only
         }
         ++turn;
