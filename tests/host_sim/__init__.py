@@ -95,3 +95,15 @@ def fisher_yates_sources(targets):
     out = np.zeros(len(targets), np.int32)
     lib().sim_fisher_yates_sources(_p(t), len(targets), _p(out))
     return out
+
+
+def handrec(cards, played, score):
+    """handrec.cuh on one hand: cards ascending (<= 10), `played` = bit mask of slots already empty."""
+    cards = np.ascontiguousarray(cards, np.uint8)
+    out = dict(find=np.zeros(256, np.int32), take_ok=np.zeros(256, np.uint8), take_meta=np.zeros(256, np.uint32), slot_card=np.zeros(10, np.uint8),
+               count=np.zeros(1, np.int32), mask=np.zeros(4, np.uint32), select=np.zeros(10, np.uint8))
+    buf = np.zeros(10, np.uint8)
+    buf[: len(cards)] = cards
+    lib().sim_handrec(_p(buf), len(cards), ctypes.c_uint32(played), ctypes.c_uint32(score), _p(out["find"]), _p(out["take_ok"]), _p(out["take_meta"]),
+                      _p(out["slot_card"]), _p(out["count"]), _p(out["mask"]), _p(out["select"]))
+    return out

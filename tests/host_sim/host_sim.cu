@@ -188,6 +188,31 @@ int sim_random_actions(int P_, int n, const int8_t* rows0, const int8_t* hands0,
     return 0;
 }
 void sim_set_form(int form) { g_form = form; }
+// handrec.cuh directly: a hand of n ascending cards with `played` slots already empty; for every card id 0..255 the slot
+// rec_find reports (-1: not dealt), whether rec_take accepts it and the meta word it would commit; then the record's
+// views: rec_card per slot, rec_count, rec_to_mask words, rec_select for every k.
+void sim_handrec(const uint8_t* cards, int n, uint32_t played, uint32_t score, int* find, uint8_t* take_ok, uint32_t* take_meta,
+                 uint8_t* slot_card, int* count, uint32_t* mask, uint8_t* select) {
+    uint32_t c[kHand];
+    for (int i = 0; i < kHand; ++i) c[i] = i < n ? cards[i] : 0;
+    HandRec h = rec_from_sorted(c, n, score);
+    h.meta |= played & kSlotBits;
+    for (int card = 0; card < 256; ++card) {
+        find[card] = rec_find(h, (uint32_t)card);
+        uint32_t meta = 0;
+        take_ok[card] = rec_take(h, (uint32_t)card, meta);
+        take_meta[card] = meta;
+    }
+    for (int i = 0; i < kHand; ++i) slot_card[i] = (uint8_t)rec_card(h, i);
+    *count = rec_count(h);
+    const uint4 m = rec_to_mask(h);
+    mask[0] = m.x; mask[1] = m.y; mask[2] = m.z; mask[3] = m.w;
+    for (int k = 0; k < *count; ++k) select[k] = (uint8_t)rec_select(h, (uint32_t)k);
+    // and back: a record rebuilt from the card set holds the same cards in the same order
+    const HandRec back = rec_from_mask(m);
+    for (int k = 0; k < *count; ++k)
+        if (rec_card(back, k) != select[k] || rec_score(back) != score) *count = -1;
+}
 // source[i] = original position of the entry that Fisher-Yates step i outputs, for steps 0..n-1 (n <= 90)
 void sim_fisher_yates_sources(const uint8_t* target, int n, int* source) {
     for (int i = 0; i < n; ++i) source[i] = fisher_yates_source<90>(target, i);

@@ -96,3 +96,40 @@ def test_illegal_moves_untouched():
     assert want["illegal"][::2].all() and want["illegal"].sum() < n
     for k in ("rewards", "done", "illegal", "hands", "boards", "scores"):
         assert (got[k] == want[k]).all(), k
+
+
+def test_hand_record_primitives_exhaustively(form):
+    """handrec.cuh (the stored form of a hand: slot search by byte tricks and multiplies, slot bits, 7-bit fields for slots
+    8 and 9) against a plain Python model, for hands of 0..10 cards with random played slots, every card id 0..255."""
+    if form != 1:
+        pytest.skip("one run is enough: the primitives do not depend on the game form")
+    from host_sim import handrec
+    rng = np.random.RandomState(12)
+    for trial in range(1500):
+        n = int(rng.randint(0, 11))
+        cards = np.sort(rng.choice(104, n, replace=False)).astype(np.uint8)
+        if trial % 7 == 0 and n:
+            cards[-1] = 103                                  # the largest card id in the last slot that holds a card
+            cards = np.unique(cards)
+            n = len(cards)
+        played = int(rng.randint(0, 1 << n)) if n else 0
+        score = int(rng.randint(0, 172))
+        out = handrec(cards, played, score)
+        held = [int(c) for i, c in enumerate(cards) if not (played >> i) & 1]
+        assert out["count"][0] == len(held)
+        assert out["select"][: len(held)].tolist() == held
+        assert out["slot_card"][:n].tolist() == cards.tolist() and (out["slot_card"][n:] >= 104).all()
+        want_mask = [0, 0, 0, 0]
+        for c in held:
+            want_mask[c >> 5] |= 1 << (c & 31)
+        want_mask[3] |= score << 24
+        assert out["mask"].tolist() == want_mask
+        for card in range(256):
+            slot = cards.tolist().index(card) if card in cards.tolist() else -1
+            assert out["find"][card] == slot, (cards, card)
+            ok = slot >= 0 and not (played >> slot) & 1
+            assert bool(out["take_ok"][card]) == ok, (cards, played, card)
+            if ok:                                           # the committed word: that slot's bit set, nothing else changed
+                others = [int(out["take_meta"][c2]) for c2 in held if c2 != card]
+                assert all((int(out["take_meta"][card]) ^ o) & 0x3FF == (1 << slot) | (1 << cards.tolist().index(c2)) for o, c2 in zip(others, [c for c in held if c != card]))
+                assert (int(out["take_meta"][card]) >> 10) & 0xFF == score
