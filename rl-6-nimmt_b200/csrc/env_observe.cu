@@ -64,8 +64,28 @@ k_observe(StateView s, T* __restrict__ obs, uint8_t* __restrict__ n_legal) {
             }
             nl[p] = cnt;
             for (int i = cnt; i < kHand; ++i) h[i] = -1;
+            // the block shared by all players of the game, behind the hand.  When a game's record is a whole number of
+            // words (P % 4 == 0) its position in the staging buffer is word aligned for every thread, and the bytes are
+            // stored as 32-bit words between the unaligned edges: a quarter of the shared-memory wavefronts of byte
+            // stores, which is what bounds the narrow-dtype observation kernel.
+            if constexpr ((P * L) % 4 == 0) {
+                const int d = p * L + 10;                    // byte offset of the common block in the record (static)
+                const int lead = (4 - (d & 3)) & 3, words = (L - 10 - lead) / 4, tail = (L - 10 - lead) % 4;
 #pragma unroll
-            for (int k = 0; k < L - 10; ++k) h[10 + k] = common[k];
+                for (int k = 0; k < lead; ++k) h[10 + k] = common[k];
+                uint32_t* w = reinterpret_cast<uint32_t*>(h + 10 + lead);
+#pragma unroll
+                for (int j = 0; j < words; ++j) {
+                    const int k = lead + 4 * j;
+                    w[j] = (uint32_t)(uint8_t)common[k] | ((uint32_t)(uint8_t)common[k + 1] << 8) | ((uint32_t)(uint8_t)common[k + 2] << 16) |
+                           ((uint32_t)(uint8_t)common[k + 3] << 24);
+                }
+#pragma unroll
+                for (int k = 0; k < tail; ++k) h[10 + lead + 4 * words + k] = common[lead + 4 * words + k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < L - 10; ++k) h[10 + k] = common[k];
+            }
         }
         if (n_legal) store_bytes<P>(n_legal, g, nl);
     }
@@ -76,10 +96,14 @@ k_observe(StateView s, T* __restrict__ obs, uint8_t* __restrict__ n_legal) {
     const int total = nb * REC;
     if (nb == TPB) {  // full block: total is a multiple of 16, the region is 16-byte aligned
         for (int e = threadIdx.x * VEC; e < total; e += TPB * VEC) {
-            alignas(16) T v[VEC];
+            if constexpr (sizeof(T) == 1) {   // int8: the staged bytes are the output
+                *reinterpret_cast<uint4*>(out + e) = *reinterpret_cast<const uint4*>(stage + e);
+            } else {
+                alignas(16) T v[VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) v[i] = obs_cast<T>(stage[e + i]);
-            *reinterpret_cast<uint4*>(out + e) = *reinterpret_cast<const uint4*>(v);
+                for (int i = 0; i < VEC; ++i) v[i] = obs_cast<T>(stage[e + i]);
+                *reinterpret_cast<uint4*>(out + e) = *reinterpret_cast<const uint4*>(v);
+            }
         }
     } else {
         for (int e = threadIdx.x; e < total; e += TPB) out[e] = obs_cast<T>(stage[e]);
