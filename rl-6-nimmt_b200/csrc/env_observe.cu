@@ -52,11 +52,50 @@ k_observe(StateView s, T* __restrict__ obs, uint8_t* __restrict__ n_legal) {
             for (int i = 0; i < 6; ++i)
                 common[n + r * 6 + i] = i < len ? (int8_t)((gm.board.cards[r] >> (8 * i)) & 0xFF) : (int8_t)-1;
         }
+        // the common block as aligned words (zero padded), for the funnel shifts below
+        constexpr int C = L - 10, CW = (C + 3) / 4;
+        uint32_t cw[CW + 1];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (4 * j + b < C) v |= (uint32_t)(uint8_t)common[4 * j + b] << (8 * b);
+            cw[j] = v;
+        }
+        cw[CW] = 0;
         int nl[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            // own hand ascending, -1 padded at the end (env.py:209-210): the unplayed slots, in slot order
             int8_t* h = rec + p * L;
+            // The block shared by all players of the game goes behind the hand, as 32-bit words: byte stores cost four
+            // times the shared-memory wavefronts, which is what bounds the narrow-dtype observation kernel.  The block
+            // starts s bytes into a word (s is the same for every thread when a record is a whole number of words, else it
+            // depends on the thread): word k of the destination holds common[4 k - s ..], a funnel shift of two
+            // neighbouring aligned words.  The first word's low s bytes land on this player's hand and are overwritten by
+            // the hand stores that follow; the bytes past the last whole word are stored one by one so that nothing of
+            // the next record is touched.
+            {
+                const uint32_t s = (uint32_t)(reinterpret_cast<uintptr_t>(h + 10) & 3u);
+                uint32_t* w = reinterpret_cast<uint32_t*>(h + 10 - s);
+                const uint32_t shift = 8u * (4u - s);          // 32 when s = 0: the clamped funnel shift returns the high word
+                constexpr int kWhole = C / 4;                  // words that are whole for every s
+#pragma unroll
+                for (int k = 0; k < kWhole; ++k) w[k] = __funnelshift_rc(k ? cw[k - 1] : 0u, cw[k], shift);
+                const uint32_t last = __funnelshift_rc(kWhole ? cw[kWhole - 1] : 0u, cw[kWhole], shift);   // common[4 kWhole - s ..]
+                const int left = C - 4 * kWhole + (int)s;     // bytes of the block that are still to be written (1 .. 4 + ..)
+                int8_t* t = reinterpret_cast<int8_t*>(w + kWhole);
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (b < left) t[b] = (int8_t)(last >> (8 * b));
+                if (left > 4) {                                // s pushed a fifth..seventh byte into one more word
+                    const uint32_t more = __funnelshift_rc(cw[kWhole], cw[kWhole + 1 <= CW ? kWhole + 1 : CW], shift);
+#pragma unroll
+                    for (int b = 0; b < 3; ++b)
+                        if (4 + b < left) t[4 + b] = (int8_t)(more >> (8 * b));
+                }
+            }
+            // own hand ascending, -1 padded at the end (env.py:209-210): the unplayed slots, in slot order
             int cnt = 0;
 #pragma unroll
             for (int i = 0; i < kHand; ++i) {
@@ -64,28 +103,6 @@ k_observe(StateView s, T* __restrict__ obs, uint8_t* __restrict__ n_legal) {
             }
             nl[p] = cnt;
             for (int i = cnt; i < kHand; ++i) h[i] = -1;
-            // the block shared by all players of the game, behind the hand.  When a game's record is a whole number of
-            // words (P % 4 == 0) its position in the staging buffer is word aligned for every thread, and the bytes are
-            // stored as 32-bit words between the unaligned edges: a quarter of the shared-memory wavefronts of byte
-            // stores, which is what bounds the narrow-dtype observation kernel.
-            if constexpr ((P * L) % 4 == 0) {
-                const int d = p * L + 10;                    // byte offset of the common block in the record (static)
-                const int lead = (4 - (d & 3)) & 3, words = (L - 10 - lead) / 4, tail = (L - 10 - lead) % 4;
-#pragma unroll
-                for (int k = 0; k < lead; ++k) h[10 + k] = common[k];
-                uint32_t* w = reinterpret_cast<uint32_t*>(h + 10 + lead);
-#pragma unroll
-                for (int j = 0; j < words; ++j) {
-                    const int k = lead + 4 * j;
-                    w[j] = (uint32_t)(uint8_t)common[k] | ((uint32_t)(uint8_t)common[k + 1] << 8) | ((uint32_t)(uint8_t)common[k + 2] << 16) |
-                           ((uint32_t)(uint8_t)common[k + 3] << 24);
-                }
-#pragma unroll
-                for (int k = 0; k < tail; ++k) h[10 + lead + 4 * words + k] = common[lead + 4 * words + k];
-            } else {
-#pragma unroll
-                for (int k = 0; k < L - 10; ++k) h[10 + k] = common[k];
-            }
         }
         if (n_legal) store_bytes<P>(n_legal, g, nl);
     }
