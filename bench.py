@@ -495,7 +495,7 @@ def run_ours(args):
         "clocks": clocks,
         "also": {"k_random_actions_ms": ra_ms, "k_deal_ms": deal_ms,
                  "fused_random_play_env_steps_per_sec": world * B / (fused_ms * 1e-3),
-                 "fused_note": "k_step<4,true>: actions drawn in-kernel, + k_deal every 10th visit; per-rank ms, not max-reduced"},
+                 "fused_note": "k_step_smem<4,true>: actions drawn in-kernel (DrunkHamster for every seat), + k_deal every 10th visit; per-rank ms, not max-reduced"},
         "alpha05": alpha,
         "mcs": {"metric": "mcs_rollouts_per_sec", "value": mcs_value, "sharded_decision_10k_per_card": sharded, "unit": "rollouts/s",
                 "config": "256 four-player opening roots x 10 candidate cards x 2000 rollouts per launch, 5 launches"},

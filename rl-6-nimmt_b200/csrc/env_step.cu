@@ -82,47 +82,71 @@ struct TileLayout {
     static_assert(kActions % 16 == 0 && kRewards % 16 == 0 && kDone % 16 == 0 && kIllegal % 16 == 0, "bulk copies need 16-byte alignment");
 };
 
-template <int P>
+// kRandom: the actions are drawn in the kernel, there is no action tape to load.
+template <int P, bool kRandom>
 __device__ __forceinline__ void issue_tile_loads(const StateView& s, const uint8_t* actions, int64_t tile, uint8_t* buf, uint64_t* bar) {
     using L = TileLayout<P>;
-    mbar_arrive_expect_tx(bar, L::kLoadBytes);
+    mbar_arrive_expect_tx(bar, kRandom ? L::kActions : L::kLoadBytes);
     bulk_load(buf, reinterpret_cast<const uint8_t*>(s.cards) + tile * L::kCardsBytes, L::kCardsBytes, bar);
     bulk_load(buf + L::kMeta, s.mut + tile * L::kMutBytes, L::kMutBytes, bar);
-    bulk_load(buf + L::kActions, actions + tile * (kTileGames * P), kTileGames * P, bar);
+    if constexpr (!kRandom) bulk_load(buf + L::kActions, actions + tile * (kTileGames * P), kTileGames * P, bar);
 }
 
 template <int P>
-__device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* rewards, uint8_t* done, uint8_t* illegal, int64_t tile,
-                                                  const uint8_t* buf) {
+__device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* rewards, uint8_t* done, uint8_t* illegal, uint8_t* actions_out,
+                                                  int64_t tile, const uint8_t* buf) {
     using L = TileLayout<P>;
     const int64_t g0 = tile * kTileGames;
     bulk_store(s.mut + tile * L::kMutBytes, buf + L::kMeta, L::kMutBytes);
     bulk_store(rewards + g0 * P, buf + L::kRewards, kTileGames * P);
     bulk_store(done + g0, buf + L::kDone, kTileGames);
     if (illegal) bulk_store(illegal + g0, buf + L::kIllegal, kTileGames);
+    if (actions_out) bulk_store(actions_out + g0 * P, buf + L::kActions, kTileGames * P);
     bulk_commit();
 }
 
 // One game, in place in the tile buffer.  `lane` selects the game.
-template <int P>
-__device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8_t* values, int* keys_w, int* keys_u) {
+// kRandom: every player plays a uniformly random card of its hand (DrunkHamster, agents/random.py:8-10), drawn exactly as
+// k_random_actions draws it (step.cuh::random_actions_game: same Philox stream, same word per player), so the fused step
+// equals k_random_actions followed by a step; the chosen slot is known, no search is needed.
+template <int P, bool kRandom>
+__device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8_t* values, int* keys_w, int* keys_u, uint64_t seed,
+                                             uint64_t game_id, uint32_t turn) {
     using L = TileLayout<P>;
     const uint2* cards0 = reinterpret_cast<const uint2*>(buf) + lane;             // + p * kTileGames
     uint32_t* meta0 = reinterpret_cast<uint32_t*>(buf + L::kMeta) + lane;         // + p * kTileGames
     uint8_t* rec = buf + L::kRows + lane * 24;
 
     int act[P];
-    load_bytes<P>(buf + L::kActions, lane, act);
-
-    // env.py:68-69 — check every card before touching anything
     uint32_t meta[P];
     bool legal = true;
+    if constexpr (kRandom) {
+        Philox rng(seed, game_id, /*stream=*/0x61637400u + turn, 0);
+        uint4 r = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-        HandRec h;
-        h.lo = cards0[p * kTileGames];
-        h.meta = meta0[p * kTileGames];
-        legal = rec_take(h, (uint32_t)act[p], meta[p]) && legal;
+        for (int p = 0; p < P; ++p) {
+            if ((p & 3) == 0) r = rng.next<7>();
+            const uint32_t word = (p & 3) == 0 ? r.x : (p & 3) == 1 ? r.y : (p & 3) == 2 ? r.z : r.w;
+            HandRec h;
+            h.lo = cards0[p * kTileGames];
+            h.meta = meta0[p * kTileGames];
+            const uint32_t n = (uint32_t)rec_count(h);
+            const uint32_t slot = select_bit32(~h.meta & kSlotBits, below(word, n ? n : 1u));
+            act[p] = n ? (int)rec_card(h, (int)slot) : 255;
+            meta[p] = h.meta | (n ? 1u << slot : 0u);
+            legal = legal && n != 0u;                      // an empty hand "plays" 255: rejected like any illegal card
+        }
+        store_bytes<P>(buf + L::kActions, lane, act);
+    } else {
+        load_bytes<P>(buf + L::kActions, lane, act);
+        // env.py:68-69 — check every card before touching anything
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            HandRec h;
+            h.lo = cards0[p * kTileGames];
+            h.meta = meta0[p * kTileGames];
+            legal = rec_take(h, (uint32_t)act[p], meta[p]) && legal;
+        }
     }
 
     // rewards default to 0 (env.py:122); a take overwrites its player's byte below
@@ -189,10 +213,10 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
     buf[L::kIllegal + lane] = !legal;
 }
 
-template <int P>
+template <int P, bool kRandom>
 __global__ void __launch_bounds__(kSmemWarps * 32, 8)
-k_step_smem(StateView s, const uint8_t* __restrict__ actions, int8_t* __restrict__ rewards, uint8_t* __restrict__ done,
-            uint8_t* __restrict__ illegal, int64_t num_tiles) {
+k_step_smem(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restrict__ actions_out, int8_t* __restrict__ rewards,
+            uint8_t* __restrict__ done, uint8_t* __restrict__ illegal, int64_t num_tiles, uint64_t seed, uint32_t turn, uint64_t game0) {
     using L = TileLayout<P>;
     extern __shared__ __align__(128) uint8_t tile_smem[];   // kSmemWarps x 2 x L::kStride
     __shared__ uint64_t full[kSmemWarps][2];
@@ -208,8 +232,8 @@ k_step_smem(StateView s, const uint8_t* __restrict__ actions, int8_t* __restrict
         mbar_init(&full[warp][0], 1);
         mbar_init(&full[warp][1], 1);
         fence_barrier_init();
-        if (tile < num_tiles) issue_tile_loads<P>(s, actions, tile, bufs, &full[warp][0]);
-        if (tile + stride < num_tiles) issue_tile_loads<P>(s, actions, tile + stride, bufs + L::kStride, &full[warp][1]);
+        if (tile < num_tiles) issue_tile_loads<P, kRandom>(s, actions, tile, bufs, &full[warp][0]);
+        if (tile + stride < num_tiles) issue_tile_loads<P, kRandom>(s, actions, tile + stride, bufs + L::kStride, &full[warp][1]);
     }
     stage_card_values(values);
     __syncthreads();   // the only block-wide barrier: value table + barrier init
@@ -218,14 +242,15 @@ k_step_smem(StateView s, const uint8_t* __restrict__ actions, int8_t* __restrict
         const int b = it & 1;
         uint8_t* buf = bufs + b * L::kStride;
         mbar_wait(&full[warp][b], (uint32_t)(it >> 1) & 1u);
-        step_in_smem<P>(buf, lane, values, reinterpret_cast<int*>(&keys_w[threadIdx.x]), reinterpret_cast<int*>(&keys_u[threadIdx.x]));
+        step_in_smem<P, kRandom>(buf, lane, values, reinterpret_cast<int*>(&keys_w[threadIdx.x]), reinterpret_cast<int*>(&keys_u[threadIdx.x]), seed,
+                                 game0 + (uint64_t)(tile * kTileGames + lane), turn);
         fence_async_smem();   // make this lane's shared-memory writes visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
-            issue_tile_stores<P>(s, rewards, done, illegal, tile, buf);
+            issue_tile_stores<P>(s, rewards, done, illegal, actions_out, tile, buf);
             if (tile + 2 * stride < num_tiles) {
                 bulk_wait_read0();   // the engine has read the buffer: it may be refilled
-                issue_tile_loads<P>(s, actions, tile + 2 * stride, buf, &full[warp][b]);
+                issue_tile_loads<P, kRandom>(s, actions, tile + 2 * stride, buf, &full[warp][b]);
             }
         }
         __syncwarp();
@@ -233,8 +258,10 @@ k_step_smem(StateView s, const uint8_t* __restrict__ actions, int8_t* __restrict
     if (lane == 0) bulk_wait_all();   // stores must land before the block's shared memory is released
 }
 
-template <int P>
-static int launch_step(const StateView& s, const uint8_t* actions, int8_t* rewards, uint8_t* done, uint8_t* illegal, cudaStream_t st) {
+// kRandom = false: actions is the tape to play; true: actions (may be NULL) receives the cards drawn in the kernel.
+template <int P, bool kRandom>
+static int launch_step(const StateView& s, uint8_t* actions, int8_t* rewards, uint8_t* done, uint8_t* illegal, uint64_t seed, uint32_t turn,
+                       uint64_t game0, cudaStream_t st) {
     using L = TileLayout<P>;
     constexpr int kSmem = kSmemWarps * 2 * L::kStride;
     const int64_t num_tiles = s.B / kTileGames;
@@ -244,19 +271,20 @@ static int launch_step(const StateView& s, const uint8_t* actions, int8_t* rewar
             int dev = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaFuncSetAttribute(k_step_smem<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+            cudaFuncSetAttribute(k_step_smem<P, kRandom>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
             int occ = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_smem<P>, kSmemWarps * 32, kSmem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_smem<P, kRandom>, kSmemWarps * 32, kSmem);
             blocks_per_sm = occ > 0 ? occ : 1;
         }
         // persistent grid: one resident wave; every warp walks tiles warp_id, warp_id + #warps, ...
         const int64_t want = (num_tiles + kSmemWarps - 1) / kSmemWarps;
         const unsigned blocks = (unsigned)min(want, (int64_t)num_sms * blocks_per_sm);
-        k_step_smem<P><<<blocks, kSmemWarps * 32, kSmem, st>>>(s, actions, rewards, done, illegal, num_tiles);
+        k_step_smem<P, kRandom><<<blocks, kSmemWarps * 32, kSmem, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, num_tiles, seed,
+                                                                        turn, game0);
     }
     const int64_t tail0 = num_tiles * kTileGames;
     if (tail0 < s.B)   // ragged tail (< 32 games): plain loads
-        k_step<P, false><<<1, kStepThreads, 0, st>>>(s, actions, nullptr, rewards, done, illegal, 0, 0, 0, tail0);
+        k_step<P, kRandom><<<1, kStepThreads, 0, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, seed, turn, game0, tail0);
     return 0;
 }
 
@@ -297,7 +325,7 @@ int nimmt_step(void* state, const uint8_t* actions, int8_t* rewards, uint8_t* do
     if (!aligned16(actions) || !aligned16(rewards) || !aligned16(done) || (illegal && !aligned16(illegal))) return NIMMT_E_ALIGN;
     if (B == 0) return NIMMT_OK;
     StateView s(state, B, num_players);
-    NIMMT_DISPATCH_P(num_players, launch_step<P>(s, actions, rewards, done, illegal, (cudaStream_t)stream));
+    NIMMT_DISPATCH_P(num_players, (launch_step<P, false>(s, const_cast<uint8_t*>(actions), rewards, done, illegal, 0, 0, 0, (cudaStream_t)stream)));
     return check_launch();
 }
 
@@ -313,11 +341,10 @@ int nimmt_step_random(void* state, uint8_t* actions, int8_t* rewards, uint8_t* d
                       uint64_t seed, uint32_t turn, uint64_t game0, void* stream) {
     if (int rc = check_common(state, B, num_players)) return rc;
     if (!rewards || !done) return NIMMT_E_BADARG;
-    if ((actions && !aligned16(actions)) || !aligned16(rewards)) return NIMMT_E_ALIGN;
+    if ((actions && !aligned16(actions)) || !aligned16(rewards) || !aligned16(done)) return NIMMT_E_ALIGN;
     if (B == 0) return NIMMT_OK;
     StateView s(state, B, num_players);
-    NIMMT_DISPATCH_P(num_players, k_step<P, true><<<blocks_for(B, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
-                                      s, nullptr, actions, rewards, done, nullptr, seed, turn, game0, 0));
+    NIMMT_DISPATCH_P(num_players, (launch_step<P, true>(s, actions, rewards, done, nullptr, seed, turn, game0, (cudaStream_t)stream)));
     return check_launch();
 }
 
