@@ -87,8 +87,7 @@ template <int P, bool kRandom>
 __device__ __forceinline__ void issue_tile_loads(const StateView& s, const uint8_t* actions, int64_t tile, uint8_t* buf, uint64_t* bar) {
     using L = TileLayout<P>;
     mbar_arrive_expect_tx(bar, kRandom ? L::kActions : L::kLoadBytes);
-    bulk_load(buf, reinterpret_cast<const uint8_t*>(s.cards) + tile * L::kCardsBytes, L::kCardsBytes, bar);
-    bulk_load(buf + L::kMeta, s.mut + tile * L::kMutBytes, L::kMutBytes, bar);
+    bulk_load(buf, s.tile_ptr(tile), L::kCardsBytes + L::kMutBytes, bar);   // the whole tile record: cards, meta words, row records
     if constexpr (!kRandom) bulk_load(buf + L::kActions, actions + tile * (kTileGames * P), kTileGames * P, bar);
 }
 
@@ -97,7 +96,7 @@ __device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* re
                                                   int64_t tile, const uint8_t* buf) {
     using L = TileLayout<P>;
     const int64_t g0 = tile * kTileGames;
-    bulk_store(s.mut + tile * L::kMutBytes, buf + L::kMeta, L::kMutBytes);
+    bulk_store(s.mut_ptr(tile), buf + L::kMeta, L::kMutBytes);
     bulk_store(rewards + g0 * P, buf + L::kRewards, kTileGames * P);
     bulk_store(done + g0, buf + L::kDone, kTileGames);
     if (illegal) bulk_store(illegal + g0, buf + L::kIllegal, kTileGames);

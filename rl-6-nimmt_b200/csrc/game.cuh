@@ -418,36 +418,35 @@ NIMMT_HD void sort_keys(int (&k)[N]) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// Packed-state addressing (include/nimmt_b200.h).  Games are stored in tiles of 32; a tile has an
-// immutable block (the dealt cards) in one array and a mutable block (slot bits + scores, row records) in another,
-// each contiguous, so that the step kernel moves a tile with one bulk copy per block:
-//     cards: [tile][P][32] uint2                       256 P bytes per tile, written by deal / reset_to only
-//     mut:   [tile]{ uint32 meta[P][32]; uint8 rows[32][24] }   128 P + 768 bytes per tile
+// Packed-state addressing (include/nimmt_b200.h).  Games are stored in tiles of 32, one contiguous record
+// per tile: an immutable block (the dealt cards) followed by a mutable block (slot bits + scores, row records), so that
+// the step kernel loads a tile with ONE bulk copy and stores its mutable tail with one:
+//     [tile]{ uint2 cards[P][32];                                  256 P bytes, written by deal / reset_to only
+//             uint32 meta[P][32]; uint8 rows[32][24] }             128 P + 768 bytes
 // A warp of 32 consecutive games reads contiguous 256- and 128-byte runs per player.
 // ----------------------------------------------------------------------------------------------
 constexpr int kTileGames = 32;
 
 struct StateView {
-    uint2* cards;
-    uint8_t* mut;
+    uint8_t* base;
     int64_t B;
     int P;
-    __host__ __device__ StateView(void* base, int64_t num_games, int num_players) : B(num_games), P(num_players) {
-        const int64_t tiles = (num_games + kTileGames - 1) / kTileGames;
-        cards = reinterpret_cast<uint2*>(base);
-        mut = reinterpret_cast<uint8_t*>(base) + tiles * cards_tile_bytes(num_players);
-    }
+    __host__ __device__ StateView(void* base_, int64_t num_games, int num_players)
+        : base(reinterpret_cast<uint8_t*>(base_)), B(num_games), P(num_players) {}
     static __host__ __device__ constexpr int64_t cards_tile_bytes(int P) { return (int64_t)P * kTileGames * 8; }
     static __host__ __device__ constexpr int64_t mut_tile_bytes(int P) { return (int64_t)P * kTileGames * 4 + kTileGames * 24; }
-    static __host__ __device__ constexpr int64_t bytes(int64_t B, int P) {
-        return (B + kTileGames - 1) / kTileGames * (cards_tile_bytes(P) + mut_tile_bytes(P));
+    static __host__ __device__ constexpr int64_t tile_bytes(int P) { return cards_tile_bytes(P) + mut_tile_bytes(P); }
+    static __host__ __device__ constexpr int64_t bytes(int64_t B, int P) { return (B + kTileGames - 1) / kTileGames * tile_bytes(P); }
+    __host__ __device__ uint8_t* tile_ptr(int64_t tile) const { return base + tile * tile_bytes(P); }
+    __host__ __device__ uint8_t* mut_ptr(int64_t tile) const { return tile_ptr(tile) + cards_tile_bytes(P); }
+    __host__ __device__ uint2* cards_ptr(int64_t g, int p) const {
+        return reinterpret_cast<uint2*>(tile_ptr(g >> 5)) + p * kTileGames + (g & 31);
     }
-    __host__ __device__ uint2* cards_ptr(int64_t g, int p) const { return cards + ((g >> 5) * P + p) * kTileGames + (g & 31); }
     __host__ __device__ uint32_t* meta_ptr(int64_t g, int p) const {
-        return reinterpret_cast<uint32_t*>(mut + (g >> 5) * mut_tile_bytes(P)) + p * kTileGames + (g & 31);
+        return reinterpret_cast<uint32_t*>(mut_ptr(g >> 5)) + p * kTileGames + (g & 31);
     }
     __host__ __device__ uint2* rows_ptr(int64_t g) const {   // three uint2 = the 24-byte row record
-        return reinterpret_cast<uint2*>(mut + (g >> 5) * mut_tile_bytes(P) + (int64_t)P * kTileGames * 4) + 3 * (g & 31);
+        return reinterpret_cast<uint2*>(mut_ptr(g >> 5) + (int64_t)P * kTileGames * 4) + 3 * (g & 31);
     }
 };
 
