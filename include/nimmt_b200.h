@@ -21,9 +21,9 @@
  *
  * Packed game state (HBM layout).  A hand only ever loses one card per step, so the ten cards a
  * player was dealt are stored once and a step writes one 32-bit word per player.  Games are stored in tiles of 32:
- *     uint2    cards[tile][P][32]   bytes 0..7 = the cards of hand slots 0..7, ascending (0x7F = none);
+ *     per tile, one contiguous record of 384 P + 768 bytes:
+ *       uint2  cards[P][32]         bytes 0..7 = the cards of hand slots 0..7, ascending (0x7F = none);
  *                                   written by deal / reset_to only
- *     per tile, contiguous:
  *       uint32 meta[P][32]          bits 0..9 slot empty (played or never dealt), bits 10..17 the player's
  *                                   cumulative Hornochsen (<= 171), bits 18..24 / 25..31 cards of slots 8 / 9
  *                                   (127 = none)
@@ -31,7 +31,7 @@
  *                                   j = 0..4; byte 20 + r = cards in the row (bits 0..2) | bull-head sum of the
  *                                   row (bits 3..7, <= 27)
  *   Total ceil(B / 32) * 32 * (12 P + 24) bytes.  A warp's accesses are contiguous in every plane and a tile is
- *   three contiguous runs of HBM.
+ *   one contiguous run of HBM.
  */
 #ifndef NIMMT_B200_H
 #define NIMMT_B200_H
