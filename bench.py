@@ -323,19 +323,25 @@ def run_ours(args):
         for st in streams:
             cap.wait_stream(st)
     g2.replay()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(K2 // CYCLE):
-        g2.replay()
-    f1.record()
-    barrier()
-    e2e_ms = f0.elapsed_time(f1)
+    # PCIe on a shared host is noisy (other tenants' traffic): K2 steps are timed three times and the MEDIAN is reported,
+    # with all three in the JSON line
+    e2e_runs = []
+    for _ in range(3):
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(K2 // CYCLE):
+            g2.replay()
+        f1.record()
+        barrier()
+        ms = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        e2e_runs.append(ms)
     assert all(int(e.illegal.any()) == 0 for e in envs) and all(bool((d == -1).all()) for d in h_done), "e2e replay diverged"
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = statistics.median(e2e_runs)
     e2e_value = world * B * K2 / (e2e_ms * 1e-3)
 
     # ---- also: the action generator alone and the fused random-play kernel (same batches, same rotation) ----
@@ -490,6 +496,7 @@ def run_ours(args):
                      "how": "CUDA events around a graph of 40 back-to-back k_step launches (4 batches x 10 turns), mean of 5",
                      "algorithmic_bytes_per_launch": bytes_per_step(P) * B, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * P, "d2h_bytes_per_step": int(h_out[0][0].numel()), "steps": K2,
+                "runs": [world * B * K2 / (m * 1e-3) for m in e2e_runs], "reported": "median of 3 runs of `steps` steps",
                 "api": "BatchedSechsNimmtEnv.step_host (pinned host actions in; rewards int8 [B,P] + done as one bit per game out in one copy), 4 batches on 4 streams, 40-step cycles replayed as a CUDA graph"},
         "gpu_launches": timed_launches,
         "clocks": clocks,
