@@ -98,8 +98,6 @@ __device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* re
     const int64_t g0 = tile * kTileGames;
     bulk_store(s.mut_ptr(tile), buf + L::kMeta, L::kMutBytes);
     bulk_store(rewards + g0 * P, buf + L::kRewards, kTileGames * P);
-    bulk_store(done + g0, buf + L::kDone, kTileGames);
-    if (illegal) bulk_store(illegal + g0, buf + L::kIllegal, kTileGames);
     if (actions_out) bulk_store(actions_out + g0 * P, buf + L::kActions, kTileGames * P);
     bulk_commit();
 }
@@ -109,8 +107,8 @@ __device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* re
 // k_random_actions draws it (step.cuh::random_actions_game: same Philox stream, same word per player), so the fused step
 // equals k_random_actions followed by a step; the chosen slot is known, no search is needed.
 template <int P, bool kRandom>
-__device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8_t* values, int* keys_w, int* keys_u, uint64_t seed,
-                                             uint64_t game_id, uint32_t turn) {
+__device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8_t* values, int* keys_w, int* keys_u, uint8_t* done_out,
+                                             uint8_t* illegal_out, uint64_t seed, uint64_t game_id, uint32_t turn) {
     using L = TileLayout<P>;
     const uint2* cards0 = reinterpret_cast<const uint2*>(buf) + lane;             // + p * kTileGames
     uint32_t* meta0 = reinterpret_cast<uint32_t*>(buf + L::kMeta) + lane;         // + p * kTileGames
@@ -208,8 +206,9 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
         *reinterpret_cast<uint32_t*>(rec + 20) = new_metas;
         done = (meta[0] & kSlotBits) == kSlotBits;     // env.py:246-249
     }
-    buf[L::kDone + lane] = done;
-    buf[L::kIllegal + lane] = !legal;
+    // the two flag bytes go out as one coalesced byte store per lane each: cheaper than two more bulk copies by lane 0
+    done_out[0] = done;
+    if (illegal_out) illegal_out[0] = !legal;
 }
 
 template <int P, bool kRandom>
@@ -241,8 +240,9 @@ k_step_smem(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restric
         const int b = it & 1;
         uint8_t* buf = bufs + b * L::kStride;
         mbar_wait(&full[warp][b], (uint32_t)(it >> 1) & 1u);
-        step_in_smem<P, kRandom>(buf, lane, values, reinterpret_cast<int*>(&keys_w[threadIdx.x]), reinterpret_cast<int*>(&keys_u[threadIdx.x]), seed,
-                                 game0 + (uint64_t)(tile * kTileGames + lane), turn);
+        const int64_t g = tile * kTileGames + lane;
+        step_in_smem<P, kRandom>(buf, lane, values, reinterpret_cast<int*>(&keys_w[threadIdx.x]), reinterpret_cast<int*>(&keys_u[threadIdx.x]), done + g,
+                                 illegal ? illegal + g : nullptr, seed, game0 + (uint64_t)g, turn);
         fence_async_smem();   // make this lane's shared-memory writes visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
