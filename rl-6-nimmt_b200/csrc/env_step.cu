@@ -50,7 +50,7 @@ k_step(StateView s, const uint8_t* __restrict__ actions_in, uint8_t* __restrict_
 
 // ------------------------------------------------------------------------------------------
 // k_step_smem — the throughput path of env.step.  HBM <-> shared memory is done entirely by the TMA
-// engine (1-D cp.async.bulk, both directions); the threads never issue a global load or store.
+// engine (1-D cp.async.bulk, both directions); the threads only store their game's few output bytes.
 //
 // Each WARP runs its own double-buffered pipeline over tiles of 32 games, with no block-level
 // synchronisation at all:
@@ -61,7 +61,8 @@ k_step(StateView s, const uint8_t* __restrict__ actions_in, uint8_t* __restrict_
 //              cards, set one bit of the player's meta word, write one card byte of the row record,
 //              add a take to the score field; the only per-row state kept in registers is the two
 //              comparison keys of game.cuh::RowKeys
-//     lane 0:  bulk-store the mutable block plus rewards / done / illegal          [bulk group]
+//     lane 0:  bulk-store the mutable block                                        [bulk group]
+//     lanes:   store their game's reward bytes and done / illegal flags (coalesced)
 // The dealt cards never travel back: a step writes 4 bytes per player instead of the 16 of a card set.
 // ------------------------------------------------------------------------------------------
 constexpr int kSmemWarps = 4;   // warps per block; each is independent
@@ -97,7 +98,6 @@ __device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* re
     using L = TileLayout<P>;
     const int64_t g0 = tile * kTileGames;
     bulk_store(s.mut_ptr(tile), buf + L::kMeta, L::kMutBytes);
-    bulk_store(rewards + g0 * P, buf + L::kRewards, kTileGames * P);
     if (actions_out) bulk_store(actions_out + g0 * P, buf + L::kActions, kTileGames * P);
     bulk_commit();
 }
@@ -107,8 +107,8 @@ __device__ __forceinline__ void issue_tile_stores(const StateView& s, int8_t* re
 // k_random_actions draws it (step.cuh::random_actions_game: same Philox stream, same word per player), so the fused step
 // equals k_random_actions followed by a step; the chosen slot is known, no search is needed.
 template <int P, bool kRandom>
-__device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8_t* values, int* keys_w, int* keys_u, uint8_t* done_out,
-                                             uint8_t* illegal_out, uint64_t seed, uint64_t game_id, uint32_t turn) {
+__device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8_t* values, int* keys_w, int* keys_u, uint8_t* rewards_out,
+                                             uint8_t* done_out, uint8_t* illegal_out, uint64_t seed, uint64_t game_id, uint32_t turn) {
     using L = TileLayout<P>;
     const uint2* cards0 = reinterpret_cast<const uint2*>(buf) + lane;             // + p * kTileGames
     uint32_t* meta0 = reinterpret_cast<uint32_t*>(buf + L::kMeta) + lane;         // + p * kTileGames
@@ -206,7 +206,13 @@ __device__ __forceinline__ void step_in_smem(uint8_t* buf, int lane, const uint8
         *reinterpret_cast<uint32_t*>(rec + 20) = new_metas;
         done = (meta[0] & kSlotBits) == kSlotBits;     // env.py:246-249
     }
-    // the two flag bytes go out as one coalesced byte store per lane each: cheaper than two more bulk copies by lane 0
+    // the per-game outputs go out as coalesced stores of the lanes (P reward bytes, two flag bytes): cheaper than three more
+    // bulk copies by lane 0
+    {
+        int rew[P];
+        load_bytes<P>(buf + L::kRewards, lane, rew);
+        store_bytes<P>(rewards_out, 0, rew);
+    }
     done_out[0] = done;
     if (illegal_out) illegal_out[0] = !legal;
 }
@@ -241,8 +247,8 @@ k_step_smem(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restric
         uint8_t* buf = bufs + b * L::kStride;
         mbar_wait(&full[warp][b], (uint32_t)(it >> 1) & 1u);
         const int64_t g = tile * kTileGames + lane;
-        step_in_smem<P, kRandom>(buf, lane, values, reinterpret_cast<int*>(&keys_w[threadIdx.x]), reinterpret_cast<int*>(&keys_u[threadIdx.x]), done + g,
-                                 illegal ? illegal + g : nullptr, seed, game0 + (uint64_t)g, turn);
+        step_in_smem<P, kRandom>(buf, lane, values, reinterpret_cast<int*>(&keys_w[threadIdx.x]), reinterpret_cast<int*>(&keys_u[threadIdx.x]),
+                                 reinterpret_cast<uint8_t*>(rewards) + g * P, done + g, illegal ? illegal + g : nullptr, seed, game0 + (uint64_t)g, turn);
         fence_async_smem();   // make this lane's shared-memory writes visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
