@@ -84,19 +84,26 @@ def test_device_rng_games_vs_oracle(P):
     assert want["done"][:, -1].all() and not want["done"][:, :-1].any()
 
 
-@pytest.mark.parametrize("P", [2, 4, 10])
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 7, 10])
 def test_step_random_equals_random_actions_then_step(P):
+    """The fused random-play step (k_step_smem<P,true> + the plain kernel on the ragged tail) against k_random_actions
+    followed by a step: same cards, rewards, done flags and state bytes every turn, with and without recording the cards;
+    one more step after the game is over changes nothing."""
     n = 4096 + 37  # ragged tail block
-    a_env, b_env = BatchedSechsNimmtEnv(n, P, seed=9), BatchedSechsNimmtEnv(n, P, seed=9)
-    a_env.reset(); b_env.reset()
+    a_env, b_env, c_env = (BatchedSechsNimmtEnv(n, P, seed=9) for _ in range(3))
+    a_env.reset(); b_env.reset(); c_env.reset()
     assert torch.equal(a_env.state, b_env.state)
-    for t in range(10):
+    for t in range(11):
         acts = a_env.random_actions()
         ra, da = a_env.step(acts)
         rb, db = b_env.step_random(record_actions=True)
-        assert torch.equal(acts, b_env._actions) and torch.equal(ra, rb) and torch.equal(da, db)
-        assert torch.equal(a_env.state, b_env.state)
-    assert bool(da.all())
+        rc, dc = c_env.step_random(record_actions=False)
+        assert torch.equal(acts, b_env._actions) and torch.equal(ra, rb) and torch.equal(da, db), t
+        assert torch.equal(ra, rc) and torch.equal(da, dc), t
+        assert torch.equal(a_env.state, b_env.state) and torch.equal(a_env.state, c_env.state), t
+        if t == 9:
+            final = a_env.state.clone()
+    assert bool(da.all()) and bool((acts == 255).all()) and torch.equal(a_env.state, final)
 
 
 @pytest.mark.parametrize("dtype", [torch.int8, torch.int16, torch.float32, torch.int64])
