@@ -32,6 +32,8 @@
  *                                   row (bits 3..7, <= 27)
  *   Total ceil(B / 32) * 32 * (12 P + 24) bytes.  A warp's accesses are contiguous in every plane and a tile is
  *   one contiguous run of HBM.
+ *   PRECONDITION of every entry point that reads `state`: it was written by nimmt_deal, nimmt_deal_from_perm or
+ *   nimmt_reset_to (an all-zero buffer is not a game: its rows have length 0 and stepping it is undefined).
  */
 #ifndef NIMMT_B200_H
 #define NIMMT_B200_H
@@ -216,10 +218,25 @@ NIMMT_API int nimmt_policy_probs(const int8_t *obs, int64_t num_decisions, const
  *   root_probs float [D][10]      policy at the root (what PUCT uses as prior; log of it is the agent's log_prob)
  * The caller applies the final rule (_choose_action_from_outcomes, agents/mcts.py:156-165) to `stats`.
  * A search is inherently sequential (PUCT reads all earlier outcomes), so one decision is never split over
- * GPUs; shard the D roots instead. */
+ * GPUs; shard the D roots instead.  n_mc <= 65535 (the root's outcome histogram counts in 16 bits); larger budgets
+ * return NIMMT_E_BADARG. */
 NIMMT_API int nimmt_policy_rollouts(const nimmt_root *roots, int num_roots, int num_players, const void *weights, int n_mc,
                                     float c_puct, int root_rule, uint64_t seed, int64_t *stats, float *root_probs,
                                     void *stream);
+
+/* PUCTAgent._choose_action_mc's root rule on its own (agents/mcts.py:276-315: _compute_pucts, _normalize_q and the strict-'>'
+ * choice), for D decisions whose rollout outcomes so far are given — the same device code nimmt_policy_rollouts runs at the
+ * root, callable (and checkable against the reference) by itself:
+ *   offsets      int32 [D+1]   outcomes of decision d are entries offsets[d] .. offsets[d+1]-1 of the two lists below
+ *   action_index int32 [...]   rank (0..9) of the first card the rollout started with, in the order the rollouts were played
+ *   outcomes     int32 [...]   the rollout's outcome (sum of player 0's rewards, in [-171, 0])
+ *   probs        float [D][10] policy prior by hand slot;  n_legal int32 [D] legal cards of the decision (1..10)
+ *   pucts        double [D][10] receives the PUCT value of every legal card (NaN where the reference yields NaN), 0 beyond
+ *   choice       int32 [D]     receives the selected hand slot
+ * At most 65535 outcomes per decision. */
+NIMMT_API int nimmt_puct_choose(const int32_t *offsets, const int32_t *action_index, const int32_t *outcomes, const float *probs,
+                                const int32_t *n_legal, int num_decisions, float c_puct, double *pucts, int32_t *choice,
+                                void *stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,7 @@ SIGNATURES = {
     "nimmt_policy_pack_weights": (_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_float, _vp]),
     "nimmt_policy_probs": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "nimmt_policy_rollouts": (_int, [_vp, _int, _int, _vp, _int, ctypes.c_float, _int, _u64, _vp, _vp, _vp]),
+    "nimmt_puct_choose": (_int, [_vp, _vp, _vp, _vp, _vp, _int, ctypes.c_float, _vp, _vp, _vp]),
 }
 
 _lib = None

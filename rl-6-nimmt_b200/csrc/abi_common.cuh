@@ -145,6 +145,33 @@ inline int check_common(const void* state, int64_t B, int P) {
         default: return NIMMT_E_BADARG;                        \
     }
 
+// Per-device launch facts.  A process may drive several GPUs (one env per device): SM counts, opt-in shared-memory sizes
+// (cudaFuncSetAttribute is per device) and occupancy are cached per device ordinal, never in a single static.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+inline int device_sms(int dev) {
+    static int sms[kMaxDevices];   // benign race: the query is idempotent
+    if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return sms[dev];
+}
+// Opts `kernel` in to `smem` bytes of dynamic shared memory on the current device (once per device) and returns how many
+// of its blocks fit on one SM.
+template <class Kernel>
+inline int blocks_per_sm_cached(Kernel kernel, int threads, int smem, int (&cache)[kMaxDevices]) {
+    const int dev = current_device();
+    if (cache[dev] == 0) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+        cache[dev] = occ > 0 ? occ : 1;
+    }
+    return cache[dev];
+}
+
 inline unsigned blocks_for(int64_t B, int threads) { return (unsigned)((B + threads - 1) / threads); }
 
 }  // namespace nimmt

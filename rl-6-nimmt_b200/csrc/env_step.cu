@@ -271,16 +271,9 @@ static int launch_step(const StateView& s, uint8_t* actions, int8_t* rewards, ui
     constexpr int kSmem = kSmemWarps * 2 * L::kStride;
     const int64_t num_tiles = s.B / kTileGames;
     if (num_tiles > 0) {
-        static int blocks_per_sm = 0, num_sms = 0;   // benign race: both queries are idempotent
-        if (blocks_per_sm == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaFuncSetAttribute(k_step_smem<P, kRandom>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-            int occ = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_smem<P, kRandom>, kSmemWarps * 32, kSmem);
-            blocks_per_sm = occ > 0 ? occ : 1;
-        }
+        static int occ_cache[kMaxDevices];   // per device: the shared-memory opt-in and the occupancy are device properties
+        const int blocks_per_sm = blocks_per_sm_cached(k_step_smem<P, kRandom>, kSmemWarps * 32, kSmem, occ_cache);
+        const int num_sms = device_sms(current_device());
         // persistent grid: one resident wave; every warp walks tiles warp_id, warp_id + #warps, ...
         const int64_t want = (num_tiles + kSmemWarps - 1) / kSmemWarps;
         const unsigned blocks = (unsigned)min(want, (int64_t)num_sms * blocks_per_sm);

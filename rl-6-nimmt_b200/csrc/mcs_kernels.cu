@@ -1,6 +1,7 @@
 // mcs_kernels.cu — Monte-Carlo search rollouts (BaseMCAgent._mcts, agents/mcts.py:91-154) for
-// batches of decisions.  Integer-issue bound: the root (64 B) is read once per block, a rollout
-// lives entirely in registers, and each block leaves three 64-bit atomics behind.
+// batches of decisions.  Integer-issue bound: the root (64 B) is read once per block; a rollout's state is ~20 registers
+// plus two private shared-memory scratch areas (its 116-byte deck and its row keys, rollout.cuh); each block leaves
+// three 64-bit atomics behind.
 #include "abi_common.cuh"
 #include "rollout.cuh"
 

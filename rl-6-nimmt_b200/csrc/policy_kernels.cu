@@ -182,13 +182,10 @@ int nimmt_policy_probs(const int8_t* obs, int64_t num_decisions, const void* wei
     if (!obs || !weights || !probs || num_decisions < 0) return NIMMT_E_BADARG;
     if (!aligned16(weights) || !aligned16(probs)) return NIMMT_E_ALIGN;
     if (num_decisions == 0) return NIMMT_OK;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_policy_probs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)policy_smem_bytes(kProbGroups));
-    }
+    if (reinterpret_cast<uintptr_t>(obs) & 3u) return NIMMT_E_ALIGN;   // the kernel reads the observations with 32-bit loads
+    static int occ_cache[kMaxDevices];
+    blocks_per_sm_cached(k_policy_probs, kTileRows * kProbGroups, (int)policy_smem_bytes(kProbGroups), occ_cache);   // per-device opt-in
+    const int num_sms = device_sms(current_device());
     const int64_t tiles = (num_decisions + kDecPerTile - 1) / kDecPerTile, ctas = (tiles + kProbGroups - 1) / kProbGroups;
     const unsigned blocks = (unsigned)(ctas < num_sms ? ctas : num_sms);   // persistent: one 4-group CTA per SM
     k_policy_probs<<<blocks, kTileRows * kProbGroups, policy_smem_bytes(kProbGroups), (cudaStream_t)stream>>>(obs, num_decisions, static_cast<const uint8_t*>(weights), probs, logits);

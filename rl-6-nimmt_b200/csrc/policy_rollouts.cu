@@ -227,15 +227,8 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
                 if (mode == kModePuct) {
                     // mcts.py:281-302: lane a computes the PUCT value of card a; the strict '>' scan over ascending cards
                     // (NaN never wins, so 0/0 everywhere picks the first card) runs on the gathered values
-                    double mine_puct = -INFINITY;
-                    if (playing && player == 0 && slot < h) mine_puct = puct_value(ts.stats, puct_bounds(ts.stats), slot, mine, c_puct);
-                    double best = -INFINITY;
-                    int choice = 0;
-#pragma unroll
-                    for (int s = 0; s < kSlots; ++s) {
-                        const double p = __shfl_sync(kFull, mine_puct, gbase + s);
-                        if (s < h && p > best) { best = p; choice = s; }
-                    }
+                    double mine_puct;
+                    const int choice = puct_choose_lanes(ts.stats, playing && player == 0, slot, h, gbase, mine, c_puct, mine_puct);
                     if (player == 0) pick = choice;
                 } else if (mode == kModeStratified) {
                     if (playing && player == 0) pick = j % h;
@@ -317,6 +310,34 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
     if (threadIdx.x < 32) tmem_dealloc(tmem_base, kTmemColsPerGroup);
 }
 
+// PUCTAgent._compute_pucts / _normalize_q / the choice (agents/mcts.py:276-315) for a batch of decisions whose outcome lists are
+// given — the root rule exactly as k_policy_rollouts evaluates it (same RootStats accumulation, same puct_choose_lanes with the
+// decision's cards in lanes 10 d .. 10 d + 9 of a warp), exposed so that it can be called and checked on its own.
+__global__ void __launch_bounds__(32)
+k_puct_cases(const int* __restrict__ offsets, const int* __restrict__ action_index, const int* __restrict__ outcomes,
+             const float* __restrict__ probs, const int* __restrict__ n_legal, int num_decisions, float c_puct, double* __restrict__ pucts,
+             int* __restrict__ choice) {
+    __shared__ RootStats st[kDecPerWarp];
+    const int lane = threadIdx.x, dloc = lane / kSlots, slot = lane % kSlots;
+    const int d = blockIdx.x * kDecPerWarp + dloc;
+    const bool live = dloc < kDecPerWarp && d < num_decisions;
+    const int gbase = (dloc < kDecPerWarp ? dloc : kDecPerWarp - 1) * kSlots;
+    if (live && slot == 0) {
+        RootStats& s = st[dloc];
+        root_stats_clear(s);
+        for (int i = offsets[d]; i < offsets[d + 1]; ++i) root_stats_add(s, action_index[i], outcomes[i]);   // agents/mcts.py:100
+    }
+    __syncwarp();
+    const int h = live ? n_legal[d] : 0;
+    const float prob = live && slot < h ? probs[(int64_t)d * kSlots + slot] : 0.0f;
+    double mine;
+    const int c = puct_choose_lanes(st[dloc < kDecPerWarp ? dloc : 0], live, slot, h, gbase, prob, c_puct, mine);
+    if (live) {
+        pucts[(int64_t)d * kSlots + slot] = slot < h ? mine : 0.0;
+        if (slot == 0) choice[d] = c;
+    }
+}
+
 }  // namespace nimmt
 
 using namespace nimmt;
@@ -325,7 +346,8 @@ extern "C" {
 
 int nimmt_policy_rollouts(const nimmt_root* roots, int num_roots, int num_players, const void* weights, int n_mc, float c_puct,
                           int mode, uint64_t seed, int64_t* stats, float* root_probs, void* stream) {
-    if (!roots || !weights || !stats || !root_probs || num_roots < 0 || n_mc < 0 || n_mc >= (1 << 24) || mode < 0 || mode > 2 ||
+    // n_mc <= 65535: the root's outcome histogram counts in 16 bits (puct.cuh::RootStats)
+    if (!roots || !weights || !stats || !root_probs || num_roots < 0 || n_mc < 0 || n_mc > 65535 || mode < 0 || mode > 2 ||
         num_players < 1 || num_players > kMaxPlayers)
         return NIMMT_E_BADARG;
     if (!aligned16(roots) || !aligned16(weights) || (reinterpret_cast<uintptr_t>(stats) & 7u)) return NIMMT_E_ALIGN;
@@ -345,6 +367,15 @@ int nimmt_policy_rollouts(const nimmt_root* roots, int num_roots, int num_player
 #undef CASE
         default: return NIMMT_E_BADARG;
     }
+    return check_launch();
+}
+
+int nimmt_puct_choose(const int32_t* offsets, const int32_t* action_index, const int32_t* outcomes, const float* probs,
+                      const int32_t* n_legal, int num_decisions, float c_puct, double* pucts, int32_t* choice, void* stream) {
+    if (!offsets || !action_index || !outcomes || !probs || !n_legal || !pucts || !choice || num_decisions < 0) return NIMMT_E_BADARG;
+    if (num_decisions == 0) return NIMMT_OK;
+    k_puct_cases<<<(unsigned)((num_decisions + kDecPerWarp - 1) / kDecPerWarp), 32, 0, (cudaStream_t)stream>>>(
+        offsets, action_index, outcomes, probs, n_legal, num_decisions, c_puct, pucts, choice);
     return check_launch();
 }
 

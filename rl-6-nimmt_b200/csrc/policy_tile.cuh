@@ -176,7 +176,7 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
         asm volatile("mov.u32 %0, 0;" : "=r"(token));
         while_mma1(token);
     }
-    mbar_wait_or_trap(bar, phase);
+    mbar_wait_mma(bar, phase);
     phase ^= 1u;
     tc_fence_after_sync();
     pc.mark(2);
@@ -206,7 +206,7 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
             umma_bf16(tmem_base, umma_desc(a2 + ks * 256, 128, kHidChunks * 128), umma_desc(w2 + ks * 256, 128, kHidChunks * 128), idesc, ks > 0);
         umma_commit(bar);
     }
-    mbar_wait_or_trap(bar, phase);
+    mbar_wait_mma(bar, phase);
     phase ^= 1u;
     tc_fence_after_sync();
     pc.mark(5);

@@ -94,4 +94,26 @@ NIMMT_HD int puct_choose(const RootStats& s, const float* probs, int n, float c_
     return choice;
 }
 
+#ifdef __CUDACC__
+// The same rule as the search kernel evaluates it (k_policy_rollouts, and k_puct_cases behind nimmt_puct_choose): the
+// decision's hand slots sit in lanes gbase .. gbase + 9 of a warp; lane `slot` computes the PUCT value of card `slot`
+// (agents/mcts.py:295-302) and every lane of the decision then runs the strict-'>' scan over the gathered values in
+// ascending card order (:286-293; NaN never wins, so 0/0 everywhere selects the first card).  All 32 lanes must call it;
+// `active` = this lane holds a legal card of a decision that is choosing.  Returns the chosen hand slot; `mine` receives this
+// lane's own PUCT value (-inf for inactive lanes).
+__device__ __forceinline__ int puct_choose_lanes(const RootStats& s, bool active, int slot, int h, int gbase, float prob, float c_puct,
+                                                 double& mine) {
+    mine = -INFINITY;
+    if (active && slot < h) mine = puct_value(s, puct_bounds(s), slot, prob, c_puct);
+    double best = -INFINITY;
+    int choice = 0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const double p = __shfl_sync(0xffffffffu, mine, gbase + i);
+        if (i < h && p > best) { best = p; choice = i; }
+    }
+    return choice;
+}
+#endif
+
 }  // namespace nimmt

@@ -82,9 +82,16 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// mbarrier wait that traps instead of hanging the GPU if the phase never completes (bring-up safety).
-__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+// Wait for an MMA-completion phase.  Product build: mbarrier.try_wait in a loop (the instruction itself suspends the thread
+// for a hardware-bounded time, so this neither burns issue slots nor can it kill the context when a profiler, a sanitizer or
+// time-slicing stretches a legitimate wait).  -DNIMMT_DEBUG_TRAP (bring-up): give up after 2^24 polls and trap instead of
+// hanging the GPU.
+__device__ __forceinline__ void mbar_wait_mma(uint64_t* bar, uint32_t parity) {
+#ifdef NIMMT_DEBUG_TRAP
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+#else
+    for (;;) {
+#endif
         uint32_t done;
         asm volatile(
             "{\n"
@@ -97,7 +104,9 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
             : "memory");
         if (done) return;
     }
+#ifdef NIMMT_DEBUG_TRAP
     __trap();
+#endif
 }
 
 }  // namespace nimmt

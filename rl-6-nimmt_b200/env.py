@@ -90,6 +90,9 @@ class BatchedSechsNimmtEnv:
             self.done = torch.zeros((B,), dtype=torch.uint8, device=self.device)
             self.illegal = torch.zeros((B,), dtype=torch.uint8, device=self.device)
             self._actions = torch.zeros((B, P), dtype=torch.uint8, device=self.device)
+            # An all-zero buffer is not a game (rows of length 0): the kernels require a state written by deal / reset_to.
+            # Deal a placeholder so that step() before reset() is merely a step of some game, never an out-of-range access.
+            N.check(self.lib.nimmt_deal(N.ptr(self.state), B, P, 0, 0, self._stream()), "nimmt_deal")
 
     # -- helpers -----------------------------------------------------------------------------
     def _stream(self):

@@ -100,6 +100,8 @@ def policy_probs(obs, weights, want_logits=False):
     lib = N.lib()
     assert obs.dtype == torch.int8 and obs.is_cuda and obs.dim() == 2 and obs.shape[1] == 47
     obs = obs.contiguous()
+    if obs.data_ptr() % 4:   # a row slice of a larger tensor: the kernel reads with 32-bit loads from a 4-byte aligned base
+        obs = obs.clone()
     D = obs.shape[0]
     probs = torch.empty((D, 10), dtype=torch.float32, device=obs.device)
     logits = torch.empty((D, 10), dtype=torch.float32, device=obs.device) if want_logits else None

@@ -1,0 +1,213 @@
+"""GPU parity tests added in round 2 ("Close the parity gaps"), all through the C ABI:
+
+  a21  the DEVICE PUCT root rule (puct.cuh::puct_choose_lanes, the code k_policy_rollouts runs) on the 40 reference cases
+  a14  BaseMCAgent's card memory — host agent AND k_mc_roots — against the set the unmodified reference agent held after
+       watching the same four turns (tests/golden/mcs_exact.json["MC3"], agents/mcts.py:62-73)
+  f3   MaskedPolicySeat probabilities on the device against tests/golden/masked_policy.npz
+  C2   the full BASELINE configs[1] size, 2^20 four-player games, every byte of every turn against the oracle
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import GOLDEN
+
+import rl_6_nimmt_b200  # noqa: F401
+from rl_6_nimmt_b200 import _native as N
+from rl_6_nimmt_b200 import policy as PL
+from rl_6_nimmt_b200 import rollouts as R
+from rl_6_nimmt_b200.agents import MCSAgent
+from rl_6_nimmt_b200.env import BatchedSechsNimmtEnv, SechsNimmtEnv
+
+pytestmark = pytest.mark.gpu
+
+
+def _puct_device(cases, c_puct=2.0):
+    offsets, idx, out, probs, n_legal = [0], [], [], np.zeros((len(cases), 10), np.float32), []
+    for d, c in enumerate(cases):
+        outcomes = {int(a): o for a, o in c["outcomes"].items()}
+        # the reference appends outcomes per card; within one card the order is the order of play, and the rule depends on the
+        # multiset only (counts, sums, min, max, median), so any interleaving gives the same answer
+        for i, a in enumerate(c["legal"]):
+            for o in outcomes[a]:
+                idx.append(i)
+                out.append(int(o))
+        offsets.append(len(idx))
+        probs[d, : len(c["legal"])] = c["probs"]
+        n_legal.append(len(c["legal"]))
+    dev = "cuda"
+    t = lambda a, dt: torch.as_tensor(np.asarray(a, dt)).to(dev)
+    offsets_d, idx_d, out_d = t(offsets, np.int32), t(idx if idx else [0], np.int32), t(out if out else [0], np.int32)
+    probs_d, n_d = torch.as_tensor(probs).to(dev), t(n_legal, np.int32)
+    pucts = torch.zeros((len(cases), 10), dtype=torch.float64, device=dev)
+    choice = torch.full((len(cases),), -1, dtype=torch.int32, device=dev)
+    N.check(N.lib().nimmt_puct_choose(N.ptr(offsets_d), N.ptr(idx_d), N.ptr(out_d), N.ptr(probs_d), N.ptr(n_d), len(cases), c_puct,
+                                      N.ptr(pucts), N.ptr(choice), N.current_stream()), "nimmt_puct_choose")
+    return pucts.cpu().numpy(), choice.cpu().numpy()
+
+
+def test_device_puct_rule_matches_the_reference_cases():
+    """a21: PUCTAgent._compute_pucts / _normalize_q / the strict-'>' choice (agents/mcts.py:276-315) as the DEVICE evaluates
+    them — fp64 on the GPU, one card per lane, shuffles, the shared-memory histogram median — against the 40 vectors generated
+    from the unmodified reference: every PUCT value to 1e-12, NaN where the reference has NaN, the choice exactly."""
+    cases = json.load(open(os.path.join(GOLDEN, "puct_cases.json")))
+    pucts, choice = _puct_device(cases)
+    n_nan = n_prior = n_median = 0
+    for d, c in enumerate(cases):
+        for a, want in enumerate(c["pucts"]):
+            if want is None:
+                assert np.isnan(pucts[d, a]), (d, a, pucts[d, a])
+                n_nan += 1
+            else:
+                assert abs(pucts[d, a] - want) < 1e-12, (d, a, pucts[d, a], want)
+        assert (pucts[d, len(c["legal"]):] == 0).all()
+        assert choice[d] == c["choice"], (d, choice[d], c["choice"])
+        total = sum(len(o) for o in c["outcomes"].values())
+        n_prior += total < 10
+        n_median += total >= 10
+    assert n_nan > 0 and n_prior > 0 and n_median > 0      # all three regimes of _normalize_q are in the fixture
+
+
+def test_device_puct_rule_random_cases_against_the_numpy_restatement():
+    """More cases than the fixture holds (odd/even outcome counts, ties, unvisited cards, every hand size), against
+    oracle/policy_oracle.py's restatement of the same lines — which the CPU suite pins to the 40 reference cases."""
+    from oracle import policy_oracle as PO
+    rng = np.random.RandomState(5)
+    cases = []
+    for _ in range(400):
+        n = int(rng.randint(1, 11))
+        legal = sorted(rng.choice(104, n, replace=False).tolist())
+        total = int(rng.choice([0, 1, 5, 9, 10, 11, 40, 199]))
+        outcomes = {a: [] for a in legal}
+        spread = int(rng.choice([0, 3, 30]))
+        for _ in range(total):
+            outcomes[legal[int(rng.randint(n))]].append(-float(rng.randint(0, spread + 1)))
+        p = rng.dirichlet(np.ones(n)).astype(np.float32)
+        cases.append({"legal": legal, "outcomes": {str(a): o for a, o in outcomes.items()}, "probs": p.tolist()})
+    pucts, choice = _puct_device(cases)
+    for d, c in enumerate(cases):
+        outcomes = {int(a): o for a, o in c["outcomes"].items()}
+        with np.errstate(all="ignore"):
+            want = PO.pucts(c["legal"], outcomes, np.asarray(c["probs"], np.float32), 2.0)
+        want_choice = PO.puct_choice(want)
+        got = pucts[d, : len(want)]
+        assert np.array_equal(np.isnan(got), np.isnan(want)), (d, got, want)
+        ok = ~np.isnan(want)
+        assert np.abs(got[ok] - want[ok]).max(initial=0.0) < 1e-12, (d, got, want)
+        assert choice[d] == want_choice, (d, choice[d], want_choice)
+
+
+def test_card_memory_matches_the_reference_agent_after_watching():
+    """a14: the reference agent watched four turns of a 3-player game dealt from np.random.seed(7) and then held exactly
+    mcs_exact.json["MC3"]["agent_available_after_watching"] (stale memory: cards played and swept within one step were never
+    seen, agents/mcts.py:62-73).  Replays the same trajectory through (i) the drop-in env + the host BaseMCAgent and (ii) the
+    batched env + k_mc_roots, and compares both with the reference's set and with the reference's observation."""
+    m = json.load(open(os.path.join(GOLDEN, "mcs_exact.json")))["MC3"]
+    P = m["P"]
+    # (i) drop-in env seeded like the fixture generator (tests/golden/make_golden.py:396-415)
+    np.random.seed(7)
+    perm = np.arange(104, dtype=np.int32)
+    np.random.shuffle(perm)
+    np.random.seed(7)
+    env = SechsNimmtEnv(P, verbose=False)
+    states, legal = env.reset()
+    agent = MCSAgent(mc_max=1, mc_per_card=1)
+    # (ii) the same deal in the batched engine (two copies, to exercise more than one game per launch)
+    benv = BatchedSechsNimmtEnv(2, P).reset_from_perm(np.stack([perm, perm]).astype(np.uint8))
+    avail = torch.zeros((2, 16), dtype=torch.uint8, device="cuda")
+    roots = torch.zeros((2, 64), dtype=torch.uint8, device="cuda")
+    lib = N.lib()
+
+    def device_memory(turn):
+        N.check(lib.nimmt_mc_roots(N.ptr(benv.state), N.ptr(avail), N.ptr(roots), 2, P, 0, int(turn == 0), N.current_stream()), "nimmt_mc_roots")
+        words = avail.cpu().numpy().view(np.uint32)
+        return [sorted(c for c in range(104) if (int(w[c >> 5]) >> (c & 31)) & 1) for w in words]
+
+    for t in range(4):
+        st = torch.tensor(states[0], dtype=torch.float)
+        if len(legal[0]) == agent.handsize:
+            agent._initialize_game(st)
+        agent._memorize_cards(st, list(map(int, legal[0])))
+        dev_sets = device_memory(t)
+        assert dev_sets[0] == dev_sets[1] == sorted(map(int, agent.available_cards)), t
+        a = [int(l[(3 * t + p) % len(l)]) for p, l in enumerate(legal)]
+        (states, legal), _, _, _ = env.step(a)
+        benv.step(torch.tensor([a, a], dtype=torch.uint8, device="cuda"), check=True)
+    assert list(map(int, states[0])) == m["state"] and list(map(int, legal[0])) == m["legal"]      # the env reproduced the reference's game
+    agent._memorize_cards(torch.tensor(states[0], dtype=torch.float), list(map(int, legal[0])))
+    assert sorted(map(int, agent.available_cards)) == m["agent_available_after_watching"]
+    dev_sets = device_memory(4)
+    assert dev_sets[0] == dev_sets[1] == m["agent_available_after_watching"]
+    # the stale set differs from what a fresh agent would believe at this state (the fixture's "available"): the test has teeth
+    assert m["agent_available_after_watching"] != m["available"]
+    # and the root the kernel would search is the one the host agent would pack
+    want = R.pack_root_from_state(np.asarray(states[0], np.float32), list(map(int, legal[0])), agent.available_cards)
+    assert (roots.cpu().numpy()[0] == want).all()
+
+
+def test_masked_policy_probabilities_on_device():
+    """f3: MaskedReinforceAgent.forward (agents/policy.py:45-60) — the 47 -> 100 -> 100 -> 104 net, normalisation without the
+    action feature, softmax over the cards in hand — evaluated on the GPU for every golden state, against the reference's own
+    probabilities (tests/golden/masked_policy.npz).  fp32 GEMMs: tolerance 2e-5 absolute."""
+    from torch import nn
+    z = np.load(os.path.join(GOLDEN, "masked_policy.npz"))
+
+    class Net(nn.Module):                                 # the reference's MultiHeadedMLP(47, (100, 100), (104,)) parameter tree
+        def __init__(self):
+            super().__init__()
+            self.latent_net = nn.Sequential(nn.Linear(47, 100), nn.ReLU(), nn.Linear(100, 100), nn.ReLU())
+            self.head_nets = nn.ModuleList([nn.Sequential(nn.Linear(100, 104))])
+
+        def forward(self, x):
+            h = self.latent_net(x)
+            return [head(h) for head in self.head_nets]
+
+    net = Net()
+    net.load_state_dict({k[len("w_actor_"):].replace("latent_net_0_", "latent_net.0.").replace("latent_net_2_", "latent_net.2.")
+                         .replace("head_nets_0_0_", "head_nets.0.0."): torch.from_numpy(z[k]) for k in z.files if k.startswith("w_actor_")})
+    net = net.cuda()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for obs in (torch.from_numpy(z["states"]).to(torch.float32).cuda(), torch.from_numpy(z["states"]).cuda()):   # float and int8 observations
+            with torch.no_grad():
+                probs = PL.masked_card_probs(net, obs).cpu().numpy()
+            assert probs.shape == z["probs"].shape
+            assert np.abs(probs - z["probs"]).max() < 2e-5, np.abs(probs - z["probs"]).max()
+            assert ((probs > 0).sum(axis=1) == z["n_legal"]).all()
+            assert np.allclose(probs.sum(axis=1), 1.0, atol=1e-5)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_full_size_replay_against_the_oracle_1m_games():
+    """BASELINE configs[1] at its full size: 2^20 four-player games dealt and played with the device RNG (k_deal,
+    k_random_actions, k_step_smem), then replayed through the C oracle — rewards, done, hands, boards and scores of every game
+    at every turn compared bit for bit (the observation kernel is what reads the device state back, so it is covered too)."""
+    n, P = 1 << 20, 4
+    env = BatchedSechsNimmtEnv(n, P, seed=20261018).reset()
+    obs0 = env.observe(dtype=torch.int8).cpu().numpy()
+    hands0, board0 = obs0[:, :, :10].copy(), obs0[:, 0, -24:].reshape(n, 4, 6).copy()
+    acts = np.zeros((n, 10, P), np.int8)
+    rewards = np.zeros((n, 10, P), np.int8)
+    done = np.zeros((n, 10), np.uint8)
+    hands = np.zeros((n, 10, P, 10), np.int8)
+    boards = np.zeros((n, 10, 4, 6), np.int8)
+    scores = np.zeros((n, 10, P), np.int16)
+    for t in range(10):
+        a = env.random_actions().clone()
+        rew, dn = env.step(a)
+        acts[:, t] = a.cpu().numpy().view(np.int8)
+        rewards[:, t], done[:, t] = rew.cpu().numpy(), dn.cpu().numpy()
+        obs = env.observe(dtype=torch.int8).cpu().numpy()
+        hands[:, t], boards[:, t] = obs[:, :, :10], obs[:, 0, -24:].reshape(n, 4, 6)
+        scores[:, t] = env.scores().cpu().numpy()
+        assert not bool(env.illegal.any())
+    want = oracle.replay(P, board0, hands0, acts, want_obs=False)
+    assert not want["illegal"].any()
+    for k, got in (("rewards", rewards), ("done", done), ("hands", hands), ("boards", boards), ("scores", scores)):
+        assert np.array_equal(got, want[k]), k
