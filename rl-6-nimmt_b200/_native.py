@@ -8,9 +8,10 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnimmt_b200.so")
+# NIMMT_B200_LIB selects another build of the same library (kernel-tuning variants, profiles/tools/build_variants.sh)
+LIB_PATH = os.environ.get("NIMMT_B200_LIB") or os.path.join(_HERE, "lib", "libnimmt_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, E_BADARG, E_ALIGN, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -3, -4
 DT_I8, DT_I16, DT_F32, DT_I64 = 0, 1, 2, 3
 ROOT_PUCT, ROOT_POLICY, ROOT_STRATIFIED = 0, 1, 2

@@ -65,48 +65,6 @@ __device__ __forceinline__ void unpack_raw(const RawGame<P>& raw, GameRec<P>& gm
                     (uint64_t)raw.rows[2].x | ((uint64_t)raw.rows[2].y << 32));
 }
 
-// P consecutive bytes at base + g * P, using the widest access the alignment of g * P guarantees
-// (base is 16-byte aligned; checked in the C entry points).
-template <int P>
-__device__ __forceinline__ void load_bytes(const uint8_t* base, int64_t g, int (&v)[P]) {
-    const uint8_t* p = base + g * P;
-    if constexpr (P % 4 == 0) {
-#pragma unroll
-        for (int i = 0; i < P / 4; ++i) {
-            const uint32_t w = reinterpret_cast<const uint32_t*>(p)[i];
-            v[4 * i] = w & 0xFF; v[4 * i + 1] = (w >> 8) & 0xFF; v[4 * i + 2] = (w >> 16) & 0xFF; v[4 * i + 3] = w >> 24;
-        }
-    } else if constexpr (P % 2 == 0) {
-#pragma unroll
-        for (int i = 0; i < P / 2; ++i) {
-            const uint32_t w = reinterpret_cast<const uint16_t*>(p)[i];
-            v[2 * i] = w & 0xFF; v[2 * i + 1] = w >> 8;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < P; ++i) v[i] = p[i];
-    }
-}
-
-template <int P>
-__device__ __forceinline__ void store_bytes(uint8_t* base, int64_t g, const int (&v)[P]) {
-    uint8_t* p = base + g * P;
-    if constexpr (P % 4 == 0) {
-#pragma unroll
-        for (int i = 0; i < P / 4; ++i)
-            reinterpret_cast<uint32_t*>(p)[i] = (uint32_t)(v[4 * i] & 0xFF) | ((uint32_t)(v[4 * i + 1] & 0xFF) << 8) |
-                                                ((uint32_t)(v[4 * i + 2] & 0xFF) << 16) | ((uint32_t)(v[4 * i + 3] & 0xFF) << 24);
-    } else if constexpr (P % 2 == 0) {
-#pragma unroll
-        for (int i = 0; i < P / 2; ++i)
-            reinterpret_cast<uint16_t*>(p)[i] = (uint16_t)((v[2 * i] & 0xFF) | ((v[2 * i + 1] & 0xFF) << 8));
-    } else {
-#pragma unroll
-        for (int i = 0; i < P; ++i) p[i] = (uint8_t)v[i];
-    }
-}
-
-
 // ------------------------------------------------------------------------------------------
 // host-side helpers of the C entry points
 // ------------------------------------------------------------------------------------------

@@ -99,7 +99,7 @@ k_observe(StateView s, T* __restrict__ obs, uint8_t* __restrict__ n_legal) {
             int cnt = 0;
 #pragma unroll
             for (int i = 0; i < kHand; ++i) {
-                if (!((gm.hand[p].meta >> i) & 1u)) h[cnt++] = (int8_t)rec_card(gm.hand[p], i);
+                if (!rec_slot_empty(gm.hand[p], i)) h[cnt++] = (int8_t)rec_card(gm.hand[p], i);
             }
             nl[p] = cnt;
             for (int i = cnt; i < kHand; ++i) h[i] = -1;

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kStepThreads) k_scores(StateView s, uint8_t* _
     if (g >= s.B) return;
     int sc[P];
 #pragma unroll
-    for (int p = 0; p < P; ++p) sc[p] = (int)((*s.meta_ptr(g, p) >> kRecScoreShift) & 0xFFu);
+    for (int p = 0; p < P; ++p) sc[p] = (int)(*s.meta_ptr(g, p) >> kRecScoreShift);
     store_bytes<P>(scores, g, sc);
 }
 
@@ -127,7 +127,7 @@ using namespace nimmt;
 
 extern "C" {
 
-int nimmt_abi_version(void) { return 2; }
+int nimmt_abi_version(void) { return 3; }
 
 const char* nimmt_last_cuda_error(void) { return g_last_error; }
 

@@ -31,6 +31,17 @@ NIMMT_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
     return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
+// PRMT: byte i of the result = byte (sel >> 4 i) & 7 of the 8-byte pair {b, a} (the sign-replication mode is not used here).
+NIMMT_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
 NIMMT_HD int imin(int a, int b) { return a < b ? a : b; }
 NIMMT_HD int imax(int a, int b) { return a > b ? a : b; }
 NIMMT_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
@@ -50,6 +61,11 @@ constexpr int kScoreShift = 24;  // score byte = bits 24..31 of hand.w (bits 120
 
 __device__ __constant__ uint8_t c_card_value[128] = {NIMMT_CARD_VALUES};
 static const uint8_t h_card_value[128] = {NIMMT_CARD_VALUES};  // host copy (nimmt_card_value, host_sim)
+
+// The same table with every value << 5 (place_v3's unit), built in shared memory from the constant table.
+__device__ __forceinline__ void stage_card_values5(uint8_t* smem) {
+    if (threadIdx.x < 128) smem[threadIdx.x] = (uint8_t)(c_card_value[threadIdx.x] << 5);
+}
 
 // Copies the 104-entry value table into shared memory (26 words -> 26 distinct banks, so a warp
 // of random lookups is conflict-free).  `smem` must hold 128 bytes.  Call before __syncthreads.
@@ -312,6 +328,48 @@ NIMMT_HD int place_indexed(int* w, int* u, int card, int value, int& row, uint32
     u[r * STRIDE] = (int)(new_sum << 2) | r;
     row = r;
     return take ? (int)sum : 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Placement, third form (the throughput kernels: k_step_tiles, k_mcs_rollouts).  Same rule as RowKeys::place, with the bit
+// fields arranged so that almost nothing has to be shifted:
+//   W[r] = top << 10 | sum << 5 | len << 2 | r        as before
+//   U[r] =             sum << 5            | r        the undercut key, its fields ALIGNED with W's
+//   key  = card << 10 | anything below bit 10         the caller keeps the player there (it never reaches W)
+//   values5[c] = bull heads of card c, << 5           (<= 7 << 5 = 224: still a byte)
+// so "which row" is sel & 3 and "the old row's bull heads" is sel & 0x3E0 whether sel came from the undercut minimum or
+// from the best row, 4 * len + r — the byte of the 24-byte row record the card lands in — is best & 0x1F, and every
+// new field is added, not shifted and or-ed.  Returns the bull heads taken, << 5 (0 if none); `row` = the row; `keep4` =
+// 4 * (cards of the row that stay under the new card) = byte offset of the card within the record, minus `row`.
+// ----------------------------------------------------------------------------------------------
+constexpr uint32_t kSumField = 0x3E0u, kLenField = 0x1Cu;
+
+NIMMT_HD uint32_t key_u_from_w(uint32_t w) { return w & (kSumField | 3u); }
+
+template <int STRIDE = 1>
+NIMMT_HD uint32_t place_v3(uint32_t* w, uint32_t* u, uint32_t key, const uint8_t* values5, uint32_t& row, uint32_t& keep4) {
+    uint4 W, U;
+    if constexpr (STRIDE == 1) {
+        W = *reinterpret_cast<const uint4*>(w);
+        U = *reinterpret_cast<const uint4*>(u);
+    } else {
+        W = make_uint4(w[0], w[STRIDE], w[2 * STRIDE], w[3 * STRIDE]);
+        U = make_uint4(u[0], u[STRIDE], u[2 * STRIDE], u[3 * STRIDE]);
+    }
+    const uint32_t dmin = umin32(umin32(key - W.x, key - W.y), umin32(key - W.z, key - W.w));   // rows above the card wrap to huge values
+    const uint32_t cheapest = umin32(umin32(U.x, U.y), umin32(U.z, U.w));
+    const bool under = dmin > key;                          // card below every top (env.py:143)
+    const uint32_t best = key - dmin;                       // == W of the row with the largest top below the card
+    const uint32_t sel = under ? cheapest : best;
+    const uint32_t r = sel & 3u, sumf = sel & kSumField, len4 = best & kLenField;
+    const bool take = under || len4 == 20u;                 // env.py:133: replaced, or the sixth card
+    keep4 = take ? 0u : len4;
+    const uint32_t base = take ? 0u : sumf;
+    const uint32_t new_u = base + values5[key >> 10] + r;
+    w[r * STRIDE] = (key & ~1023u) + new_u + keep4 + 4u;
+    u[r * STRIDE] = new_u;
+    row = r;
+    return sumf - base;                                     // the row's sum BEFORE the append (env.py:164), << 5
 }
 
 struct Board {

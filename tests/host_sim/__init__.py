@@ -15,7 +15,7 @@ def lib():
     if _lib is None:
         src = os.path.join(_HERE, "host_sim.cu")
         csrc = os.path.join(_HERE, "..", "..", "rl-6-nimmt_b200", "csrc")
-        newest = max(os.path.getmtime(p) for p in [src] + [os.path.join(csrc, f) for f in ("game.cuh", "handrec.cuh", "step.cuh", "rollout.cuh", "puct.cuh")])
+        newest = max(os.path.getmtime(p) for p in [src] + [os.path.join(csrc, f) for f in ("game.cuh", "handrec.cuh", "step.cuh", "step_tile.cuh", "rollout.cuh", "puct.cuh")])
         if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < newest:
             subprocess.check_call(["nvcc", "-O1", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
                                    "-Wno-deprecated-gpu-targets", "-o", _LIB, src])
@@ -26,7 +26,8 @@ def lib():
 
 
 def set_form(form):
-    """0: the per-game logic on 104-bit card sets (Game<P>); 1: on the stored hand records (GameRec<P>, handrec.cuh)."""
+    """0: the per-game logic on 104-bit card sets (Game<P>); 1: on the stored hand records (GameRec<P>, handrec.cuh);
+    2: in place in 32-game tile records through step_tile.cuh::step_lane, the per-lane code of k_step_tiles."""
     lib().sim_set_form(int(form))
 
 
@@ -43,6 +44,20 @@ def replay(P, rows0, hands0, actions):
                hands=np.zeros((n, T, P, 10), np.int8), boards=np.zeros((n, T, 4, 6), np.int8), scores=np.zeros((n, T, P), np.int16))
     rc = lib().sim_replay(P, n, T, _p(rows0), _p(hands0), _p(actions), _p(out["rewards"]), _p(out["done"]), _p(out["illegal"]),
                           _p(out["hands"]), _p(out["boards"]), _p(out["scores"]))
+    assert rc == 0
+    return out
+
+
+def play_random_tiles(P, rows0, hands0, turns, seed, game0=0):
+    """Random-vs-random play through the fused per-lane step (step_lane<P, true>).  Returns replay()'s dict plus the cards drawn."""
+    rows0 = np.ascontiguousarray(rows0, np.int8)
+    hands0 = np.ascontiguousarray(hands0, np.int8)
+    n, T = len(rows0), turns
+    out = dict(actions=np.zeros((n, T, P), np.int8), rewards=np.zeros((n, T, P), np.int8), done=np.zeros((n, T), np.uint8),
+               illegal=np.zeros((n, T), np.uint8), hands=np.zeros((n, T, P, 10), np.int8), boards=np.zeros((n, T, 4, 6), np.int8),
+               scores=np.zeros((n, T, P), np.int16))
+    rc = lib().sim_play_random_tiles(P, n, T, _p(rows0), _p(hands0), ctypes.c_uint64(seed), ctypes.c_uint64(game0), _p(out["actions"]),
+                                     _p(out["rewards"]), _p(out["done"]), _p(out["illegal"]), _p(out["hands"]), _p(out["boards"]), _p(out["scores"]))
     assert rc == 0
     return out
 

@@ -7,6 +7,7 @@
 #include "../../rl-6-nimmt_b200/csrc/puct.cuh"
 #include "../../rl-6-nimmt_b200/csrc/rollout.cuh"
 #include "../../rl-6-nimmt_b200/csrc/step.cuh"
+#include "../../rl-6-nimmt_b200/csrc/step_tile.cuh"
 
 using namespace nimmt;
 
@@ -51,7 +52,7 @@ static void init_game(GameRec<P>& r, const int8_t* rows0, const int8_t* hands0) 
     r.board = g.board;
 }
 
-static int g_form = 0;   // 0: card sets (Game<P>), 1: stored form (GameRec<P>)
+static int g_form = 0;   // 0: card sets (Game<P>), 1: stored form (GameRec<P>), 2: in place in a tile record (step_tile.cuh, what k_step_tiles runs)
 
 template <int P>
 static void init_game(Game<P>& g, const int8_t* rows0 /*[4][6]*/, const int8_t* hands0 /*[P][10]*/) {
@@ -87,6 +88,72 @@ static void replay(int n, int turns, const int8_t* rows0, const int8_t* hands0, 
             done[gt] = game_done<P>(g);
             for (int p = 0; p < P; ++p) rewards[gt * P + p] = (int8_t)(-pen[p]);
             unpack_to_arrays<P>(g, hands + gt * P * 10, boards + gt * 24, scores + gt * P);
+        }
+    }
+}
+
+
+// ---- form 2: the games live in tile records (32 games per tile, exactly the HBM / shared-memory layout) and are stepped in
+// place by step_tile.cuh::step_lane, the per-lane code of k_step_tiles ----
+template <int P>
+static void tile_put(uint8_t* tile, int lane, const GameRec<P>& r) {
+    using L = TileLayout<P>;
+    for (int p = 0; p < P; ++p) {
+        reinterpret_cast<uint2*>(tile)[p * kTileGames + lane] = r.hand[p].lo;
+        reinterpret_cast<uint32_t*>(tile + L::kMeta)[p * kTileGames + lane] = r.hand[p].meta;
+    }
+    uint64_t q[3];
+    r.board.pack(q[0], q[1], q[2]);
+    memcpy(tile + L::kRows + lane * 24, q, 24);
+}
+template <int P>
+static void tile_get(const uint8_t* tile, int lane, GameRec<P>& r) {
+    using L = TileLayout<P>;
+    for (int p = 0; p < P; ++p) {
+        r.hand[p].lo = reinterpret_cast<const uint2*>(tile)[p * kTileGames + lane];
+        r.hand[p].meta = reinterpret_cast<const uint32_t*>(tile + L::kMeta)[p * kTileGames + lane];
+    }
+    uint64_t q[3];
+    memcpy(q, tile + L::kRows + lane * 24, 24);
+    r.board.unpack(q[0], q[1], q[2]);
+}
+
+// kRandom: `actions` is OUTPUT (the cards the fused random step drew), keyed (seed, game0 + game, turn0 + t).
+template <int P, bool kRandom>
+static void replay_tiles(int n, int turns, const int8_t* rows0, const int8_t* hands0, int8_t* actions, int8_t* rewards, uint8_t* done,
+                         uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores, uint64_t seed, uint64_t game0) {
+    using L = TileLayout<P>;
+    alignas(16) static uint8_t tile[L::kTileBytes];
+    alignas(16) uint8_t acts[L::kActBytes];
+    uint8_t values5[128];
+    for (int c = 0; c < 128; ++c) values5[c] = (uint8_t)(h_card_value[c] << 5);
+    for (int first = 0; first < n; first += kTileGames) {
+        const int lanes = n - first < kTileGames ? n - first : kTileGames;
+        memset(tile, 0, sizeof(tile));
+        for (int lane = 0; lane < lanes; ++lane) {
+            GameRec<P> r;
+            init_game<P>(r, rows0 + (size_t)(first + lane) * 24, hands0 + (size_t)(first + lane) * P * 10);
+            tile_put<P>(tile, lane, r);
+        }
+        for (int t = 0; t < turns; ++t) {
+            for (int lane = 0; lane < lanes; ++lane) {
+                const size_t gt = (size_t)(first + lane) * turns + t;
+                if (!kRandom)
+                    for (int p = 0; p < P; ++p) acts[lane * P + p] = (uint8_t)actions[gt * P + p];
+                alignas(16) uint32_t kw[4], ku[4];
+                uint8_t rew[P], dn = 0, ill = 0, drawn[P];
+                step_lane<P, kRandom>(tile, acts, lane, values5, kw, ku, rew, &dn, &ill, kRandom ? drawn : nullptr, seed, game0 + (uint64_t)(first + lane),
+                                      (uint32_t)t);
+                for (int p = 0; p < P; ++p) {
+                    rewards[gt * P + p] = (int8_t)rew[p];
+                    if (kRandom) actions[gt * P + p] = (int8_t)drawn[p];
+                }
+                done[gt] = dn;
+                illegal[gt] = ill;
+                GameRec<P> r;
+                tile_get<P>(tile, lane, r);
+                unpack_to_arrays<P>(r, hands + gt * P * 10, boards + gt * 24, scores + gt * P);
+            }
         }
     }
 }
@@ -172,8 +239,16 @@ int sim_mcs(int P_, const nimmt_root* root, int64_t R, uint64_t seed, int rank, 
 }
 int sim_replay(int P_, int n, int turns, const int8_t* rows0, const int8_t* hands0, const int8_t* actions, int8_t* rewards,
                uint8_t* done, uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores) {
-    if (g_form) { DISPATCH(P_, (replay<P, GameRec<P>>(n, turns, rows0, hands0, actions, rewards, done, illegal, hands, boards, scores))); }
+    if (g_form == 2) {
+        DISPATCH(P_, (replay_tiles<P, false>(n, turns, rows0, hands0, const_cast<int8_t*>(actions), rewards, done, illegal, hands, boards, scores, 0, 0)));
+    } else if (g_form) { DISPATCH(P_, (replay<P, GameRec<P>>(n, turns, rows0, hands0, actions, rewards, done, illegal, hands, boards, scores))); }
     else { DISPATCH(P_, (replay<P, Game<P>>(n, turns, rows0, hands0, actions, rewards, done, illegal, hands, boards, scores))); }
+    return 0;
+}
+// Random-vs-random play through the fused per-lane step (step_lane<P, true>): `actions` receives the cards drawn.
+int sim_play_random_tiles(int P_, int n, int turns, const int8_t* rows0, const int8_t* hands0, uint64_t seed, uint64_t game0, int8_t* actions,
+                          int8_t* rewards, uint8_t* done, uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores) {
+    DISPATCH(P_, (replay_tiles<P, true>(n, turns, rows0, hands0, actions, rewards, done, illegal, hands, boards, scores, seed, game0)));
     return 0;
 }
 int sim_deal(int P_, int n, uint64_t seed, uint64_t game0, int8_t* hands, int8_t* boards) {
@@ -196,12 +271,12 @@ void sim_handrec(const uint8_t* cards, int n, uint32_t played, uint32_t score, i
     uint32_t c[kHand];
     for (int i = 0; i < kHand; ++i) c[i] = i < n ? cards[i] : 0;
     HandRec h = rec_from_sorted(c, n, score);
-    h.meta |= played & kSlotBits;
+    h.meta |= rec_spread(played & kSlotBits);
     for (int card = 0; card < 256; ++card) {
         find[card] = rec_find(h, (uint32_t)card);
         uint32_t meta = 0;
         take_ok[card] = rec_take(h, (uint32_t)card, meta);
-        take_meta[card] = meta;
+        take_meta[card] = rec_empties(meta) | ((meta >> kRecScoreShift) << 10);   // canonical view: slot-order empty bits | score << 10
     }
     for (int i = 0; i < kHand; ++i) slot_card[i] = (uint8_t)rec_card(h, i);
     *count = rec_count(h);

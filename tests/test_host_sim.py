@@ -8,13 +8,14 @@ import pytest
 
 import oracle
 from conftest import GOLDEN
-from host_sim import deal, lib, random_actions, replay, set_form
+from host_sim import deal, lib, play_random_tiles, random_actions, replay, set_form
 
 
-@pytest.fixture(autouse=True, params=[0, 1], ids=["card-sets", "stored-records"])
+@pytest.fixture(autouse=True, params=[0, 1, 2], ids=["card-sets", "stored-records", "tile-records"])
 def form(request):
-    """Every test runs on both forms of the per-game logic: 104-bit card sets (Game<P>) and the stored hand records
-    the kernels step in place (GameRec<P>, handrec.cuh)."""
+    """Every test runs on all forms of the per-game logic: 104-bit card sets (Game<P>), the stored hand records
+    (GameRec<P>, handrec.cuh), and 32-game tile records stepped in place by step_tile.cuh::step_lane — the exact per-lane
+    code of the throughput kernel k_step_tiles (placement by game.cuh::place_v3)."""
     set_form(request.param)
     yield request.param
     set_form(0)
@@ -82,6 +83,30 @@ def test_random_games_vs_oracle(P):
     assert want["done"][:, -1].all() and not want["done"][:, :-1].any()
 
 
+@pytest.mark.parametrize("P", [1, 2, 4, 5, 7, 10])
+def test_fused_random_step_in_tiles(P, form):
+    """step_lane<P, true> (the fused random-play step of k_step_tiles): draws the cards k_random_actions would draw for the
+    same (seed, game, turn), and steps them exactly as the oracle does; 70 games = two full tiles and a ragged one."""
+    if form != 2:
+        pytest.skip("tile form only")
+    n = 70
+    hands, boards = deal(P, n, seed=31 + P)
+    got = play_random_tiles(P, boards, hands, 10, seed=8, game0=1000)
+    cur_h, cur_b = hands, boards
+    for t in range(10):
+        a = random_actions(P, cur_b, cur_h, seed=8, turn=t, game0=1000)
+        assert (a.astype(np.int8) == got["actions"][:, t]).all(), t
+        step = oracle.replay(P, cur_b, cur_h, got["actions"][:, t:t + 1], want_obs=False)
+        cur_h, cur_b = step["hands"][:, 0], step["boards"][:, 0]
+    want = oracle.replay(P, boards, hands, got["actions"], want_obs=False)
+    for k in ("rewards", "done", "illegal", "hands", "boards", "scores"):
+        assert (got[k] == want[k]).all(), k
+    # past the end of the game: empty hands "play" 255, the step is rejected and nothing changes
+    more = play_random_tiles(P, want["boards"][:, -1], want["hands"][:, -1], 1, seed=8, game0=1000)
+    assert more["illegal"].all() and (more["actions"].view(np.uint8) == 255).all() and (more["rewards"] == 0).all()
+    assert (more["boards"][:, 0] == want["boards"][:, -1]).all()
+
+
 def test_illegal_moves_untouched():
     P, n = 4, 500
     hands, boards = deal(P, n, seed=3)
@@ -89,8 +114,10 @@ def test_illegal_moves_untouched():
     bad = acts.copy()
     # every 2nd game: player 2 plays a card that sits on the board
     bad[::2, 0, 2] = boards[::2, 1, 0]
-    # every 5th game: out-of-range card id
+    # every 5th game: out-of-range card id (104..127 match no stored card; >= 128 is rejected before the byte tricks)
     bad[::5, 0, 0] = 120
+    bad[::15, 0, 0] = -56     # 200
+    bad[7::30, 0, 3] = 127    # the "no card" pattern itself
     want = oracle.replay(P, boards, hands, bad, want_obs=False)
     got = replay(P, boards, hands, bad)
     assert want["illegal"][::2].all() and want["illegal"].sum() < n
