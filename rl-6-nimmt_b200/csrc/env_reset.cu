@@ -9,19 +9,63 @@ thread_local char g_last_error[256] = "";
 // ------------------------------------------------------------------------------------------
 // k_deal — SechsNimmtEnv.reset/_deal (env.py:43-51, 99-112).  Write-only: (12 P + 24) B/game.
 // ------------------------------------------------------------------------------------------
-constexpr int kDealThreads = 64;   // 104 words x 64 threads = 26 KB of interleaved decks per block
+// One thread per game.  The per-thread decks are BYTES, interleaved so that every entry of a thread lives in that thread's
+// own bank: entry j of thread (warp w, lane l) sits at byte 128 j + 4 l + w — a block of four warps shares 104 x 32 words,
+// each word holding the same entry of the four warps' lane-l games.  A random access is conflict-free whatever it draws, its
+// address is one multiply-add, and a deck costs 104 bytes of shared memory (the first version used a 32-bit word per
+// card: 416 bytes per thread, 16 warps per SM).  The identity is written cooperatively, 26 words per thread.
+// Finished hands and rows go straight to HBM (coalesced: a warp's games are contiguous in every plane).
+constexpr int kDealThreads = 128;
+
+template <int P>
+struct DealToState {
+    const StateView& s;
+    int64_t g;
+    const uint8_t* values;
+    uint32_t row_cards = 0, row_metas = 0;
+    __device__ __forceinline__ void hand(int p, const uint32_t (&c)[kHand]) {
+        // rec_from_sorted for a full hand of ten: slots 0..7 in the uint2, slots 8 and 9 in the low bytes of the meta word
+        *s.cards_ptr(g, p) = make_uint2(c[0] | (c[1] << 8) | (c[2] << 16) | (c[3] << 24), c[4] | (c[5] << 8) | (c[6] << 16) | (c[7] << 24));
+        *s.meta_ptr(g, p) = c[8] | (c[9] << 8);
+    }
+    // two sorted hands, 16 bits per card, hand p in the low halves: every record word is gathered with byte permutes
+    // (byte 0 / byte 2 of each register; bytes 1 and 3 are zero and serve as the zero source)
+    __device__ __forceinline__ void hand_pair(int p, const Pair16 (&k)[kHand]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t pick = h ? 0x0062u : 0x0040u;   // {a.b0, b.b0} or {a.b2, b.b2} into the low half
+            const uint32_t x = __byte_perm(__byte_perm(k[0].v, k[1].v, pick), __byte_perm(k[2].v, k[3].v, pick), 0x5410u);
+            const uint32_t y = __byte_perm(__byte_perm(k[4].v, k[5].v, pick), __byte_perm(k[6].v, k[7].v, pick), 0x5410u);
+            *s.cards_ptr(g, p + h) = make_uint2(x, y);
+            *s.meta_ptr(g, p + h) = __byte_perm(k[8].v, k[9].v, h ? 0x1162u : 0x1140u);   // slots 8, 9; no empty bits, score 0
+        }
+    }
+    __device__ __forceinline__ void row(int r, uint32_t card) {
+        row_cards |= card << (8 * r);
+        row_metas |= (1u | ((uint32_t)values[card] << 3)) << (8 * r);   // one card, its bull heads
+        if (r == kRows - 1) {   // slot-major record: byte r = first card of row r, bytes 4..19 unused, bytes 20..23 the row metas
+            uint2* rec = s.rows_ptr(g);
+            rec[0] = make_uint2(row_cards, 0u);
+            rec[1] = make_uint2(0u, 0u);
+            rec[2] = make_uint2(0u, row_metas);
+        }
+    }
+};
 
 template <int P>
 __global__ void __launch_bounds__(kDealThreads) k_deal(StateView s, uint64_t seed, uint64_t game0) {
     __shared__ uint8_t values[128];
-    __shared__ uint32_t decks[kCards * kDealThreads];
+    __shared__ __align__(16) uint8_t decks[kCards * kDealThreads];
     stage_card_values(values);
+    {   // word k = entry k / 32 of four games = that card id in all four bytes; thread t writes words t, t + 128, ...
+        uint32_t v = (threadIdx.x >> 5) * 0x01010101u;
+#pragma unroll
+        for (int k = 0; k < kCards * 32 / kDealThreads; ++k, v += (kDealThreads / 32) * 0x01010101u) reinterpret_cast<uint32_t*>(decks)[k * kDealThreads + threadIdx.x] = v;
+    }
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * kDealThreads + threadIdx.x;
     if (g >= s.B) return;
-    GameRec<P> gm;
-    deal_game<P>(gm, seed, game0 + (uint64_t)g, values, decks + threadIdx.x, kDealThreads);
-    store_game<P>(s, g, gm);
+    deal_game<P>(seed, game0 + (uint64_t)g, decks + (threadIdx.x & 31) * 4 + (threadIdx.x >> 5), 128, DealToState<P>{s, g, values});
 }
 
 // k_deal_from_perm — the same, from caller-supplied shuffled decks (env.py:103-112).

@@ -64,7 +64,7 @@ static const uint8_t h_card_value[128] = {NIMMT_CARD_VALUES};  // host copy (nim
 
 // The same table with every value << 5 (place_v3's unit), built in shared memory from the constant table.
 __device__ __forceinline__ void stage_card_values5(uint8_t* smem) {
-    if (threadIdx.x < 128) smem[threadIdx.x] = (uint8_t)(c_card_value[threadIdx.x] << 5);
+    for (uint32_t c = threadIdx.x; c < 128u; c += blockDim.x) smem[c] = (uint8_t)(c_card_value[c] << 5);   // any block size
 }
 
 // Copies the 104-entry value table into shared memory (26 words -> 26 distinct banks, so a warp
@@ -441,8 +441,23 @@ NIMMT_HD void cswap(int& a, int& b) {
     b = hi;
 }
 
-template <int N>
-NIMMT_HD void sort_keys(int (&k)[N]) {
+// Two 16-bit keys per word, compared lane-wise (VIMNMX.U16x2): one network sorts two independent sequences at once.
+struct Pair16 {
+    uint32_t v;
+};
+NIMMT_HD void cswap(Pair16& a, Pair16& b) {
+#ifdef __CUDA_ARCH__
+    const uint32_t lo = __vminu2(a.v, b.v), hi = __vmaxu2(a.v, b.v);
+#else
+    const uint32_t al = a.v & 0xFFFFu, ah = a.v >> 16, bl = b.v & 0xFFFFu, bh = b.v >> 16;
+    const uint32_t lo = (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16), hi = (al < bl ? bl : al) | ((ah < bh ? bh : ah) << 16);
+#endif
+    a.v = lo;
+    b.v = hi;
+}
+
+template <int N, class T>
+NIMMT_HD void sort_keys(T (&k)[N]) {
 #define CS(i, j) cswap(k[i], k[j])
     if constexpr (N == 2) {
         CS(0, 1);

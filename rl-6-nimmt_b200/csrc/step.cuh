@@ -153,33 +153,18 @@ NIMMT_HD bool game_done(const GameRec<P>& g) { return rec_empty(g.hand[0]); }
 // 104-card deck, 10 P + 4 draws.  Draw i < 10 P goes to hand i / 10 (the reference's
 // perm[10p .. 10p+9]), draw 10 P + r opens row r (the reference's perm[103 - r]): a prefix plus
 // four more entries of a uniform permutation, which is all the reference's shuffle provides.
-// `deck` is the game's private 104-entry scratch, one 32-bit word per card at a stride of `deck_stride` words: on the
-// device the block's decks are interleaved (entry j of thread t at word j * threads + t), so the 32 games of a warp hit
-// 32 different banks whatever positions they draw (byte decks at a per-thread stride cost ~3.5 wavefronts per access).
-
-// The ten cards dealt to player p (any order) become its hand.
-template <int P>
-NIMMT_HD void set_dealt_hand(Game<P>& g, int p, int (&cards)[kHand]) {
-    uint4 h = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < kHand; ++i) mask_set(h, (uint32_t)cards[i]);
-    g.hand[p] = h;
-}
-template <int P>
-NIMMT_HD void set_dealt_hand(GameRec<P>& g, int p, int (&cards)[kHand]) {
-    sort_keys<kHand>(cards);   // the reference sorts each hand (env.py:105); slots are in ascending card order
-    uint32_t c[kHand];
-#pragma unroll
-    for (int i = 0; i < kHand; ++i) c[i] = (uint32_t)cards[i];
-    g.hand[p] = rec_from_sorted(c, kHand, 0u);
-}
-
-template <int P, class G>
-NIMMT_HD void deal_game(G& g, uint64_t seed, uint64_t game_id, const uint8_t* values, uint32_t* deck, int deck_stride) {
+//   deck         the game's private 104-entry scratch, one BYTE per card at a stride of `deck_stride` bytes, already
+//                holding the identity (entry j = card j).  On the device the decks of a block are interleaved so that a
+//                thread's entries all live in its own shared-memory bank (env_reset.cu): a warp's 32 games hit 32
+//                different banks whatever positions they draw.
+//   sink         receives the result as it is produced: ten cards per hand in ASCENDING order (the reference sorts each hand,
+//                env.py:105) and sink.row(r, card).  Hands are sorted two at a time — both sequences ride in one register
+//                per position, 16 bits each, through one comparator network (game.cuh::Pair16) — and handed over in that
+//                form, sink.hand_pair(p, k); the last hand of an odd table arrives as sink.hand(p, cards).
+// Uniform integers by 32-bit multiply-high, two per random word (below_keep): one Philox4x32-7 call serves eight cards.
+template <int P, class Sink>
+NIMMT_HD void deal_game(uint64_t seed, uint64_t game_id, uint8_t* deck, int deck_stride, Sink&& sink) {
     Philox rng(seed, game_id, /*stream=*/0x6e696d74u, 0);
-#pragma unroll
-    for (int i = 0; i < kCards; ++i) deck[i * deck_stride] = (uint32_t)i;
-    // two draws per 32-bit word (below_keep): one Philox4x32-7 call serves eight cards
     uint4 r = make_uint4(0, 0, 0, 0);
     uint32_t spare = 0;
     auto draw = [&](int i) -> uint32_t {
@@ -191,23 +176,78 @@ NIMMT_HD void deal_game(G& g, uint64_t seed, uint64_t game_id, const uint8_t* va
         } else {
             off = below(spare, (uint32_t)(kCards - i));
         }
-        const uint32_t j = (uint32_t)i + off;
-        const uint32_t card = deck[j * deck_stride];
-        deck[j * deck_stride] = deck[i * deck_stride];   // position i is never read again, so only half of the swap is needed
+        uint8_t* at = deck + i * deck_stride + off * (uint32_t)deck_stride;   // entry j = i + off
+        const uint32_t card = *at;
+        *at = deck[i * deck_stride];   // position i is never read again, so only half of the swap is needed
         return card;
     };
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-        int cards[kHand];
+    for (int p = 0; p + 1 < P; p += 2) {   // hands p and p + 1 together
+        Pair16 k[kHand];
 #pragma unroll
-        for (int i = 0; i < kHand; ++i) cards[i] = (int)draw(p * kHand + i);
-        set_dealt_hand<P>(g, p, cards);
+        for (int i = 0; i < kHand; ++i) k[i].v = draw(p * kHand + i);
+#pragma unroll
+        for (int i = 0; i < kHand; ++i) k[i].v += draw((p + 1) * kHand + i) << 16;
+        sort_keys<kHand>(k);
+        sink.hand_pair(p, k);   // hand p in the low halves, hand p + 1 in the high halves
+    }
+    if constexpr (P % 2 == 1) {
+        int k[kHand];
+#pragma unroll
+        for (int i = 0; i < kHand; ++i) k[i] = (int)draw((P - 1) * kHand + i);
+        sort_keys<kHand>(k);
+        uint32_t a[kHand];
+#pragma unroll
+        for (int i = 0; i < kHand; ++i) a[i] = (uint32_t)k[i];
+        sink.hand(P - 1, a);
     }
 #pragma unroll
-    for (int row = 0; row < kRows; ++row) {
-        const uint32_t card = draw(P * kHand + row);
-        g.board.set_row(row, card, card, 1u, values[card]);
+    for (int row = 0; row < kRows; ++row) sink.row(row, draw(P * kHand + row));
+}
+
+// Sinks that fill a game held in registers (tests/host_sim; the kernel stores straight to HBM instead).
+template <int P>
+struct DealIntoGame {
+    Game<P>& g;
+    const uint8_t* values;
+    NIMMT_HD void hand(int p, const uint32_t (&cards)[kHand]) {
+        uint4 h = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < kHand; ++i) mask_set(h, cards[i]);
+        g.hand[p] = h;
     }
+    NIMMT_HD void hand_pair(int p, const Pair16 (&k)[kHand]) {
+        uint32_t a[kHand], b[kHand];
+#pragma unroll
+        for (int i = 0; i < kHand; ++i) { a[i] = k[i].v & 0xFFFFu; b[i] = k[i].v >> 16; }
+        hand(p, a);
+        hand(p + 1, b);
+    }
+    NIMMT_HD void row(int r, uint32_t card) { g.board.set_row(r, card, card, 1u, values[card]); }
+};
+template <int P>
+struct DealIntoGameRec {
+    GameRec<P>& g;
+    const uint8_t* values;
+    NIMMT_HD void hand(int p, const uint32_t (&cards)[kHand]) { g.hand[p] = rec_from_sorted(cards, kHand, 0u); }
+    NIMMT_HD void hand_pair(int p, const Pair16 (&k)[kHand]) {
+        uint32_t a[kHand], b[kHand];
+#pragma unroll
+        for (int i = 0; i < kHand; ++i) { a[i] = k[i].v & 0xFFFFu; b[i] = k[i].v >> 16; }
+        hand(p, a);
+        hand(p + 1, b);
+    }
+    NIMMT_HD void row(int r, uint32_t card) { g.board.set_row(r, card, card, 1u, values[card]); }
+};
+
+// The ten cards dealt to player p (any order) become its hand (deal from caller-supplied decks, env_reset.cu).
+template <int P>
+NIMMT_HD void set_dealt_hand(GameRec<P>& g, int p, int (&cards)[kHand]) {
+    sort_keys<kHand>(cards);   // the reference sorts each hand (env.py:105); slots are in ascending card order
+    uint32_t c[kHand];
+#pragma unroll
+    for (int i = 0; i < kHand; ++i) c[i] = (uint32_t)cards[i];
+    g.hand[p] = rec_from_sorted(c, kHand, 0u);
 }
 
 // DrunkHamster.forward (agents/random.py:8-10): a uniform card of each non-empty hand.

@@ -3,6 +3,7 @@
 // oracle without a GPU.  It is never linked into libnimmt_b200.so and never used as a fallback.
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 
 #include "../../rl-6-nimmt_b200/csrc/puct.cuh"
 #include "../../rl-6-nimmt_b200/csrc/rollout.cuh"
@@ -163,8 +164,10 @@ static void deal(int n, uint64_t seed, uint64_t game0, int8_t* hands, int8_t* bo
     int16_t sc[P];
     for (int gi = 0; gi < n; ++gi) {
         G g;
-        uint32_t deck[kCards];
-        deal_game<P>(g, seed, game0 + gi, h_card_value, deck, 1);
+        uint8_t deck[kCards];
+        for (int c = 0; c < kCards; ++c) deck[c] = (uint8_t)c;
+        if constexpr (std::is_same<G, Game<P>>::value) deal_game<P>(seed, game0 + gi, deck, 1, DealIntoGame<P>{g, h_card_value});
+        else deal_game<P>(seed, game0 + gi, deck, 1, DealIntoGameRec<P>{g, h_card_value});
         unpack_to_arrays<P>(g, hands + (size_t)gi * P * 10, boards + (size_t)gi * 24, sc);
     }
 }
