@@ -157,6 +157,17 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def moved_bytes_per_step(P):
+    """HBM bytes the shipped layout really moves per env step: read the tile record (12 P + 24) and P action
+    bytes, write the mutable block (4 P + 24), P reward bytes, the done and the illegal flag."""
+    return (12 * P + 24) + P + (4 * P + 24) + P + 2
+
+
+def pack_roots(R, np, obs, P):
+    return np.stack([R.pack_root([[int(c) for c in row if c >= 0] for row in o[0, -24:].reshape(4, 6)], [int(c) for c in o[0, :10]],
+                                 [c for c in range(104) if c not in set(o[0, :10].tolist()) | set(o[0, -24:].tolist())], P) for o in obs])
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -164,7 +175,7 @@ def run_ours(args):
 
     import rl_6_nimmt_b200  # noqa: F401
     from rl_6_nimmt_b200 import rollouts as R
-    from rl_6_nimmt_b200.env import BatchedSechsNimmtEnv
+    from rl_6_nimmt_b200.env import BatchedSechsNimmtEnv, SechsNimmtEnv
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,6 +193,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(*vals):
+        if world == 1:
+            return vals if len(vals) > 1 else vals[0]
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out = [float(x) for x in t]
+        return out if len(out) > 1 else out[0]
+
+    def event_ms(fn):
+        """CUDA-event time of fn() on the current stream, bracketed by barrier + synchronize, max over ranks."""
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b))
+
+    peaks, peak_kind = measured_peaks()
     P, B, K, W = NUM_PLAYERS, GAMES, args.steps, args.warmup
     # games are independent: rank r owns global games [r * NSETS * B, (r + 1) * NSETS * B) — no data-path collective
     envs = [BatchedSechsNimmtEnv(B, P, seed=1234, game0=(rank * NSETS + s) * B) for s in range(NSETS)]
@@ -196,95 +226,114 @@ def run_ours(args):
         env.turn = 10
     launches = 0
 
-    def one_step(i, ev=None):
+    def one_step(i):
         nonlocal launches
         env, tape = envs[i % NSETS], tapes[i % NSETS]
         if env.turn == 10:
             env.reset(seed=env.seed)   # same seed => same deal => the recorded actions stay legal
             launches += 1
-        if ev is not None:
-            ev[0].record()
         env.step(tape[env.turn])
-        if ev is not None:
-            ev[1].record()
         launches += 1
 
     CYCLE = NSETS * 10   # steps after which every batch has played one full game and sits at turn 10 again
 
-    for i in range(max(W, 3)):
+    def capture(n_steps, first=0):
+        """A CUDA graph of steps first .. first + n_steps - 1 of the cycle (the loop is launch-bound from Python: a step is
+        ~25 us of GPU work); returns (graph, launches in it)."""
+        nonlocal launches
+        g = torch.cuda.CUDAGraph()
+        before = launches
+        with torch.cuda.graph(g):
+            for i in range(first, first + n_steps):
+                one_step(i)
+        return g, launches - before
+
+    for i in range(max(W, 3)):          # warm-up steps, eager
         one_step(i)
     for i in range((-max(W, 3)) % CYCLE):   # untimed: bring every batch back to a game boundary
         one_step(max(W, 3) + i)
     barrier()
-    # The inner loop is launch-bound from Python (a k_step launch is ~35 us of GPU time), so one
-    # cycle of 40 steps + 4 re-deals is captured once into a CUDA graph and replayed.
-    graph = torch.cuda.CUDAGraph()
-    launches = 0
-    with torch.cuda.graph(graph):
-        for i in range(CYCLE):
-            one_step(i)
-    launches_per_cycle = launches
-    for env in envs:
-        env.turn = 10
-    graph.replay()   # warm the instantiated graph
+    # EXACTLY K steps are timed, always as graph replays: K // 40 replays of the whole 40-step cycle (4 re-deals) plus one
+    # graph holding the K % 40 remaining steps; an untimed third graph finishes the cycle so that every repetition starts
+    # at a game boundary.  The timed region is repeated REPS times and the median is reported.
+    g_cycle, n_cycle = capture(CYCLE)
+    rem = K % CYCLE
+    g_rem, n_rem = capture(rem) if rem else (None, 0)
+    g_fin, _ = capture(CYCLE - rem, first=rem) if rem else (None, 0)
+    g_cycle.replay()
     barrier()
+    REPS = 7
+
+    def timed_region():
+        for _ in range(K // CYCLE):
+            g_cycle.replay()
+        if g_rem is not None:
+            g_rem.replay()
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
-    launches = 0
-    barrier()
+        time.sleep(0.3)
     t_begin = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K // CYCLE):
-        graph.replay()
-    for env in envs:
-        env.turn = 10
-    for i in range(K % CYCLE):   # the remainder, eagerly: exactly K steps are timed
-        one_step(i)
-    e1.record()
-    barrier()
+    region_ms = []
+    for _ in range(REPS):
+        region_ms.append(event_ms(timed_region))
+        if g_fin is not None:
+            g_fin.replay()
+    # keep the GPU under the same load until the clock sampler has a few samples inside the measured window
+    while time.perf_counter() - t_begin < 0.8:
+        g_cycle.replay()
+        torch.cuda.synchronize()
     t_end = time.perf_counter()
-    elapsed_ms = e0.elapsed_time(e1)
-    timed_launches = launches + (K // CYCLE) * launches_per_cycle
-    illegal = sum(int(e.illegal.any()) for e in envs)
-    assert illegal == 0, "random legal actions were rejected"
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    assert sum(int(e.illegal.any()) for e in envs) == 0, "random legal actions were rejected"
+    elapsed_ms = statistics.median(region_ms)
+    timed_launches = (K // CYCLE) * n_cycle + n_rem
     value = world * B * K / (elapsed_ms * 1e-3)
 
     # ---- the dominant kernel on its own: the same cycle split into two graphs, the 4 re-deals and the
     # 40 k_step launches, with CUDA events around the latter.  (Events around every single launch add
-    # ~5 us each to a ~34 us kernel, and eager launches from Python cannot keep the queue full.) ----
-    for i in range((-(K % CYCLE)) % CYCLE):
-        one_step((K % CYCLE) + i)
-    barrier()
+    # ~5 us each to a ~25 us kernel, and eager launches from Python cannot keep the queue full.) ----
+    for env in envs:
+        env.turn = 10
     g_deal, g_steps = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
     with torch.cuda.graph(g_deal):
         for env in envs:
             env.reset(seed=env.seed)
     with torch.cuda.graph(g_steps):
         for i in range(CYCLE):
-            env = envs[i % NSETS]
-            env.step(tapes[i % NSETS][i // NSETS])
-    reps = 5
-    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            envs[i % NSETS].step(tapes[i % NSETS][i // NSETS])
     g_deal.replay(); g_steps.replay()
-    barrier()
-    for a, b_ in pairs:
-        g_deal.replay()
-        a.record()
-        g_steps.replay()
-        b_.record()
-    barrier()
+    kstep_runs, kdeal_runs = [], []
+    for _ in range(7):
+        kdeal_runs.append(event_ms(g_deal.replay) / NSETS)
+        kstep_runs.append(event_ms(g_steps.replay) / CYCLE)
     assert sum(int(e.illegal.any()) for e in envs) == 0
+    kstep_ms, kdeal_ms = statistics.median(kstep_runs), statistics.median(kdeal_runs)
+
+    # ---- step + observe (SURVEY §8d: "report step-only and step+observe separately"; the reference rebuilds all P observations
+    # inside every step, env.py:73): the same cycle with k_observe after every step, int8 and fp32 observations ----
+    step_obs = {}
+    for name, dt in (("i8", torch.int8), ("f32", torch.float32)):
+        obs_buf = [torch.empty((B, P, 47), dtype=dt, device=dev) for _ in range(NSETS)]
+        for env in envs:
+            env.turn = 10
+        g_so = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_so):
+            for i in range(CYCLE):
+                env = envs[i % NSETS]
+                if env.turn == 10:
+                    env.reset(seed=env.seed)
+                env.step(tapes[i % NSETS][env.turn])
+                env.observe(out=obs_buf[i % NSETS])
+        g_so.replay()
+        ms = statistics.median(event_ms(g_so.replay) for _ in range(5)) / CYCLE
+        bytes_alg = bytes_per_step(P) + 47 * P * obs_buf[0].element_size() + (12 * P + 24)
+        step_obs[name] = {"env_steps_per_sec": world * B / (ms * 1e-3), "ms_per_step": ms, "hbm_frac": bytes_alg * B / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                          "bytes_per_step": bytes_alg}
+        del obs_buf, g_so
     for env in envs:
         env.turn = 10
-    kstep_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in pairs) / CYCLE
 
     # ---- end to end: host buffers in, host buffers out, every step ---------------------------------
     # Legal action sequences are recorded once (untimed) into pinned host memory by playing each
@@ -300,8 +349,7 @@ def run_ours(args):
             h_actions[s][t].copy_(a)
             env.step(a)
     torch.cuda.synchronize()
-    K2 = max(NSETS * 10, min(K, 2000))
-    K2 -= K2 % (NSETS * 10)
+    K2 = max(CYCLE, min(K - K % CYCLE, 2000))
 
     def e2e_cycle():
         """One full game of every batch through the host-buffer API, each batch on its own stream:
@@ -323,96 +371,81 @@ def run_ours(args):
         for st in streams:
             cap.wait_stream(st)
     g2.replay()
-    # PCIe on a shared host is noisy (other tenants' traffic): K2 steps are timed three times and the MEDIAN is reported,
-    # with all three in the JSON line
-    e2e_runs = []
-    for _ in range(3):
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(K2 // CYCLE):
-            g2.replay()
-        f1.record()
-        barrier()
-        ms = f0.elapsed_time(f1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        e2e_runs.append(ms)
+    # PCIe on a shared host is noisy (other tenants' traffic): K2 steps are timed five times and the MEDIAN is reported,
+    # with all runs in the JSON line
+    e2e_runs = [event_ms(lambda: [g2.replay() for _ in range(K2 // CYCLE)]) for _ in range(5)]
     assert all(int(e.illegal.any()) == 0 for e in envs) and all(bool((d == -1).all()) for d in h_done), "e2e replay diverged"
     e2e_ms = statistics.median(e2e_runs)
     e2e_value = world * B * K2 / (e2e_ms * 1e-3)
 
-    # ---- also: the action generator alone and the fused random-play kernel (same batches, same rotation) ----
-    def timed(fn, n):
-        for i in range(NSETS):
-            fn(i)
-        barrier()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda._sleep(int(4e7))   # hold the GPU while the host enqueues: measures kernels, not launch latency
-        a.record()
-        for i in range(n):
-            fn(i)
-        b_.record()
-        barrier()
-        return a.elapsed_time(b_) / n
+    # ---- also: the action generator alone, the fused random-play kernel, the B = 1 drop-in ----
+    def graph_ms(fn, launches_in_graph, reps=5):
+        fn()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        g.replay()
+        return statistics.median(event_ms(g.replay) for _ in range(reps)) / launches_in_graph
 
     for env in envs:
         env.reset(seed=env.seed)
-    ra_ms = timed(lambda i: envs[i % NSETS].random_actions(out=tapes[i % NSETS][0], turn=0), 200)
+    ra_ms = graph_ms(lambda: [envs[i % NSETS].random_actions(out=tapes[i % NSETS][0], turn=0) for i in range(3 * NSETS)], 3 * NSETS)
 
-    def fused(i):
-        env = envs[i % NSETS]
-        if env.turn == 10:
-            env.reset()
-        env.step_random()
-    fused_ms = timed(fused, 400)
-    deal_ms = timed(lambda i: envs[i % NSETS].reset(), 100)
+    def fused_cycle():
+        for env in envs:
+            env.reset(seed=env.seed)
+        for t in range(10):
+            for env in envs:
+                env.step_random()
+    fused_ms = graph_ms(fused_cycle, CYCLE)     # per env step, re-deals included
+
+    facade_us = None
+    if rank == 0:
+        # the B = 1 drop-in (SechsNimmtEnv: reference signatures, numpy in and out), random legal play, wall clock incl. every sync
+        np.random.seed(0)
+        env1 = SechsNimmtEnv(P, verbose=False, device=dev)
+        n_steps, t0 = 0, None
+        for game in range(6):
+            states, legal = env1.reset()
+            if game == 1:
+                torch.cuda.synchronize(); t0 = time.perf_counter(); n_steps = 0
+            done = False
+            while not done:
+                (states, legal), _, done, _ = env1.step([l[np.random.randint(len(l))] for l in legal])
+                n_steps += 1
+        facade_us = 1e6 * (time.perf_counter() - t0) / n_steps
 
     # ---- secondary metric: MCS rollouts/s (BASELINE configs[2] shape: 4 players, 10 candidate cards) ---
     obs0 = BatchedSechsNimmtEnv(256, P, seed=5, game0=rank * 256).reset().observe(dtype=torch.int8).cpu().numpy()
-    roots = np.stack([R.pack_root([[int(c) for c in row if c >= 0] for row in o[0, -24:].reshape(4, 6)], [int(c) for c in o[0, :10]],
-                                  [c for c in range(104) if c not in set(o[0, :10].tolist()) | set(o[0, -24:].tolist())], P) for o in obs0])
+    roots = pack_roots(R, np, obs0, P)
     roots_d = torch.as_tensor(roots).to(dev)
     per_action = 2000
     stats = torch.zeros((256, 10, 3), dtype=torch.int64, device=dev)
     for _ in range(3):
         R.mcs_rollouts(roots_d, P, per_action, seed=1, out=stats)
-    barrier()
-    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
-    m0.record()
-    for r in range(reps):
-        R.mcs_rollouts(roots_d, P, per_action, seed=2 + r, out=stats)
-    m1.record()
-    barrier()
-    mcs_ms = m0.elapsed_time(m1)
-    if world > 1:
-        t = torch.tensor([mcs_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        mcs_ms = float(t.item())
+    mcs_ms = statistics.median(event_ms(lambda: [R.mcs_rollouts(roots_d, P, per_action, seed=2 + r, out=stats) for r in range(reps)]) for _ in range(3))
     mcs_value = world * reps * 256 * 10 * per_action / (mcs_ms * 1e-3)
+    mcs_per_gpu = mcs_value / world
+    int_peak = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6          # thread-instructions/s at the maximum SM clock
+    mcs_roofline = {"bound": "int-issue", "achieved": mcs_per_gpu * 40 * 64, "peak": int_peak, "unit": "thread-inst/s",
+                    "frac": mcs_per_gpu * 40 * 64 / int_peak, "traffic": None, "kernel": "k_mcs_rollouts<4>",
+                    "how": "SURVEY.md 8d: rollouts/s x n P placements (40) x the 64-instruction algorithmic budget per placement, over 148 SMs x 128 lanes x the maximum SM clock; per GPU"}
 
     # BASELINE configs[2] itself: ONE decision batch (the same roots on every rank), 10,000 rollouts per candidate card,
     # rollout ids striped over the ranks, then the path's only collective (int64 [D,10,3] all-reduce over NCCL / NVLink)
     shard_obs = BatchedSechsNimmtEnv(4096, P, seed=6, game0=0).reset().observe(dtype=torch.int8).cpu().numpy()
-    shard_roots = torch.as_tensor(np.stack([R.pack_root([[int(c) for c in row if c >= 0] for row in o[0, -24:].reshape(4, 6)], [int(c) for c in o[0, :10]],
-                                  [c for c in range(104) if c not in set(o[0, :10].tolist()) | set(o[0, -24:].tolist())], P) for o in shard_obs])).to(dev)
+    shard_roots = torch.as_tensor(pack_roots(R, np, shard_obs, P)).to(dev)
     sharded = {}
+    table = None
     for D, reps_d in ((1, 20), (4096, 2)):
         R.sharded_mcs_rollouts(shard_roots[:D], P, 10_000, seed=1, device=dev)
-        barrier()
-        m0.record()
-        for r in range(reps_d):
-            table = R.sharded_mcs_rollouts(shard_roots[:D], P, 10_000, seed=2 + r, device=dev)
-        m1.record()
-        barrier()
-        ms_d = m0.elapsed_time(m1) / reps_d
-        if world > 1:
-            t = torch.tensor([ms_d], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_d = float(t.item())
+
+        def run_d():
+            nonlocal table
+            for r in range(reps_d):
+                table = R.sharded_mcs_rollouts(shard_roots[:D], P, 10_000, seed=2 + r, device=dev)
+        ms_d = statistics.median(event_ms(run_d) for _ in range(3)) / reps_d
         assert int(table[:, :, 2].sum()) == D * 10 * 10_000       # every rollout of every candidate was played exactly once
         sharded[f"D{D}"] = {"ms_per_decision_batch": ms_d, "rollouts_per_sec": D * 10 * 10_000 / (ms_d * 1e-3)}
 
@@ -421,28 +454,11 @@ def run_ours(args):
     torch.manual_seed(0)
     blob = PL.pack_weights(PL.PolicyNet(), device=dev)
     R.policy_rollouts(roots_d, P, blob, 200, seed=1)
-    barrier()
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record()
-    for r in range(3):
-        R.policy_rollouts(roots_d, P, blob, 200, seed=2 + r)
-    a1.record()
-    barrier()
-    puct_ms = a0.elapsed_time(a1) / 3
+    puct_ms = statistics.median(event_ms(lambda: R.policy_rollouts(roots_d, P, blob, 200, seed=2 + r)) for r in range(3))
     # batched leaf evaluation: the policy for every seat of 2^18 games (2^20 decisions, ~8.9e6 rows of 48 features)
     obs_all = envs[0].reset(seed=77).observe(dtype=torch.int8).reshape(-1, 47)[: 1 << 20].contiguous()
     PL.policy_probs(obs_all, blob)
-    barrier()
-    a0.record()
-    for r in range(3):
-        PL.policy_probs(obs_all, blob)
-    a1.record()
-    barrier()
-    leaf_ms = a0.elapsed_time(a1) / 3
-    if world > 1:
-        t = torch.tensor([puct_ms, leaf_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        puct_ms, leaf_ms = float(t[0]), float(t[1])
+    leaf_ms = statistics.median(event_ms(lambda: PL.policy_probs(obs_all, blob)) for _ in range(3))
     # the whole self-play loop of configs[3]: 256 games, four PUCT seats sharing one net (mc_max = 200, run.py), every
     # search on chip, one batched imitation step per iteration
     from rl_6_nimmt_b200.play import BatchedGameSession, PolicySeat
@@ -450,62 +466,99 @@ def run_ours(args):
     sp_net = PL.PolicyNet()
     session = BatchedGameSession([PolicySeat(sp_net, mc_max=200, puct=True, learn=True) for _ in range(P)], 256, device=dev, seed=7)
     session.play_games()
-    barrier()
-    a0.record()
-    for r in range(2):
-        session.play_games()
-    a1.record()
-    barrier()
-    selfplay_ms = a0.elapsed_time(a1) / 2
-    if world > 1:
-        t = torch.tensor([selfplay_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        selfplay_ms = float(t.item())
+    selfplay_ms = statistics.median(event_ms(session.play_games) for _ in range(2))
     rows_per_rollout = P * sum(range(1, 11))           # 220 policy rows in a full 4-player rollout
     flop_per_row = 2 * (48 * 100 + 100 * 100 + 100)    # un-padded, SURVEY.md §8d
+    search_tflops = 256 * 200 * rows_per_rollout * flop_per_row / (puct_ms * 1e-3) / 1e12          # per GPU
+    leaf_tflops = float((obs_all[:, :10] >= 0).sum()) * flop_per_row / (leaf_ms * 1e-3) / 1e12      # per GPU
     alpha = {
         "puct_rollouts_per_sec": world * 256 * 200 / (puct_ms * 1e-3), "ms_per_256_decisions": puct_ms,
         "config": "256 PUCT searches per GPU (4-player opening roots, 10 legal cards), 200 sequential rollouts each, random-init policy net (torch.manual_seed(0))",
-        "policy_tflops_in_search": world * 256 * 200 * rows_per_rollout * flop_per_row / (puct_ms * 1e-3) / 1e12,
+        "policy_tflops_in_search": world * search_tflops,
         "selfplay_games_per_sec": world * 256 / (selfplay_ms * 1e-3), "selfplay_ms_per_256_games": selfplay_ms,
         "selfplay_config": "256 four-player games per GPU, every seat a PUCT agent (mc_max 200) on one shared net, 36 search launches + one batched imitation step (Adam) per iteration",
         "leaf_eval_decisions_per_sec": world * (1 << 20) / (leaf_ms * 1e-3),
-        "leaf_eval_tflops": world * float((obs_all[:, :10] >= 0).sum()) * flop_per_row / (leaf_ms * 1e-3) / 1e12,
+        "leaf_eval_tflops": world * leaf_tflops,
+        "roofline": {"bound": "tensor", "achieved": search_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": search_tflops / peaks["bf16_tflops"],
+                     "traffic": None, "kernel": "k_policy_rollouts<4>",
+                     "how": "un-padded FLOPs (29,800 per policy row x 220 rows per 4-player rollout) over the CUDA-event time of one launch, per GPU; a search is latency-bound (sequential rollouts), see DESIGN.md 5.4",
+                     "leaf_eval": {"kernel": "k_policy_probs", "achieved": leaf_tflops, "frac": leaf_tflops / peaks["bf16_tflops"]}},
     }
+
+    # ---- BASELINE configs[4]: ten-player max-table sweep, the games split evenly over the ranks (weak per-rank timing, max over ranks) ----
+    sweep = []
+    free_bytes = torch.cuda.mem_get_info(dev)[0]
+    del envs, tapes, h_actions, h_out, streams, g_cycle, g_rem, g_fin, g_deal, g_steps, g2, session
+    torch.cuda.empty_cache()
+    for lg in args.sweep_log2:
+        total_games = 1 << lg
+        Bs = total_games // world
+        need = Bs * (12 * 10 + 24 + 10 + 10 + 2) * 1.05
+        if need > 0.8 * torch.cuda.mem_get_info(dev)[0]:
+            sweep.append({"games": total_games, "skipped": "does not fit one GPU's share of HBM"})
+            continue
+        nsets = max(1, min(4, -(-3 * 126_000_000 // (Bs * 144))))       # rotate batches until the L2 cannot hold them
+        es = [BatchedSechsNimmtEnv(Bs, 10, seed=21 + s, game0=(rank * nsets + s) * Bs) for s in range(nsets)]
+        acts = [torch.empty((Bs, 10), dtype=torch.uint8, device=dev) for _ in range(nsets)]
+        step_ms = deal_ms = 0.0
+        for rep in range(2):    # the first pass warms up
+            deal_ms = event_ms(lambda: [e.reset(seed=e.seed) for e in es]) / nsets
+            step_ms = 0.0
+            for t in range(10):
+                for e, a in zip(es, acts):
+                    e.random_actions(out=a)
+                step_ms += event_ms(lambda: [e.step(a) for e, a in zip(es, acts)]) / nsets
+        assert all(bool(e.done.all()) and not bool(e.illegal.any()) for e in es)
+        step_ms /= 10
+        sweep.append({"games": total_games, "games_per_gpu": Bs, "batches_per_gpu": nsets, "k_step_ms": step_ms, "k_deal_ms": deal_ms,
+                      "env_steps_per_sec": world * Bs / (step_ms * 1e-3),
+                      "frac_canonical": bytes_per_step(10) * Bs / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "frac_moved": moved_bytes_per_step(10) * Bs / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]})
+        del es, acts
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peaks, peak_kind = measured_peaks()
     achieved = bytes_per_step(P) * B / (kstep_ms * 1e-3) / 1e9
-    traffic = None
+    moved = moved_bytes_per_step(P) * B / (kstep_ms * 1e-3) / 1e9
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("k_step_p4_dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic, traffic_note = tj.get("k_step_p4_dram_bytes_per_launch"), tj.get("note_short")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "players": P, "games_per_gpu_per_step": B,
                    "l2": f"{NSETS} independent batches visited round-robin ({NSETS} x {(12 * P + 24 + 2 * P + 2) * B / 1e6:.0f} MB > 126 MB L2), no explicit flush",
-                   "step": "k_step over recorded uniformly random legal actions resident in HBM, + k_deal every 10th visit of a batch; 40-step cycles replayed as a CUDA graph", "seed": 1234},
+                   "step": "k_step over recorded uniformly random legal actions resident in HBM, + k_deal every 10th visit of a batch; the K timed steps are CUDA-graph replays (whole 40-step cycles + one graph of the K % 40 remainder)", "seed": 1234},
+        "timed_region_ms": elapsed_ms, "timed_region_runs_ms": region_ms, "timed_region_reported": f"median of {REPS} repetitions of exactly {K} steps",
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": traffic, "kernel": "k_step_smem<4>", "kernel_ms": kstep_ms,
-                     "how": "CUDA events around a graph of 40 back-to-back k_step launches (4 batches x 10 turns), mean of 5",
+                     "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_step_tiles<4>", "kernel_ms": kstep_ms,
+                     "frac_canonical": achieved / peaks["hbm_gbs"], "frac_moved": moved / peaks["hbm_gbs"], "achieved_moved": moved,
+                     "moved_bytes_per_launch": moved_bytes_per_step(P) * B,
+                     "how": "CUDA events around a graph of 40 back-to-back k_step launches (4 batches x 10 turns), median of 7; `frac` = SURVEY 8d's canonical 193 B/step, `frac_moved` = the 122 B/step the shipped layout really moves",
                      "algorithmic_bytes_per_launch": bytes_per_step(P) * B, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * P, "d2h_bytes_per_step": int(h_out[0][0].numel()), "steps": K2,
-                "runs": [world * B * K2 / (m * 1e-3) for m in e2e_runs], "reported": "median of 3 runs of `steps` steps",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * P, "d2h_bytes_per_step": (B * P + 15) // 16 * 16 + 4 * ((B + 31) // 32), "steps": K2,
+                "runs": [world * B * K2 / (m * 1e-3) for m in e2e_runs], "reported": "median of 5 runs of `steps` steps",
                 "api": "BatchedSechsNimmtEnv.step_host (pinned host actions in; rewards int8 [B,P] + done as one bit per game out in one copy), 4 batches on 4 streams, 40-step cycles replayed as a CUDA graph"},
         "gpu_launches": timed_launches,
         "clocks": clocks,
-        "also": {"k_random_actions_ms": ra_ms, "k_deal_ms": deal_ms,
+        "also": {"k_random_actions_ms": ra_ms, "k_deal_ms": kdeal_ms,
                  "fused_random_play_env_steps_per_sec": world * B / (fused_ms * 1e-3),
-                 "fused_note": "k_step_smem<4,true>: actions drawn in-kernel (DrunkHamster for every seat), + k_deal every 10th visit; per-rank ms, not max-reduced"},
+                 "fused_note": "k_step_tiles<4,true>: actions drawn in-kernel (DrunkHamster for every seat), + k_deal every 10th visit; max over ranks",
+                 "step_plus_observe_i8": step_obs["i8"], "step_plus_observe_f32": step_obs["f32"],
+                 "step_plus_observe_note": "k_step + k_observe of all P seats after every step (+ k_deal every 10th), the reference's own step semantics (env.py:73); hbm_frac = algorithmic bytes (193 + 47 P sizeof + 12 P + 24) over the cycle time",
+                 "b1_facade_us_per_step": facade_us,
+                 "b1_facade_note": "SechsNimmtEnv (the B = 1 drop-in with the reference's signatures) playing random legal cards, wall clock per env.step incl. observation rebuild and host syncs; the Python reference takes ~130 us per 4-player step (BASELINE.md)"},
         "alpha05": alpha,
         "mcs": {"metric": "mcs_rollouts_per_sec", "value": mcs_value, "sharded_decision_10k_per_card": sharded, "unit": "rollouts/s",
-                "config": "256 four-player opening roots x 10 candidate cards x 2000 rollouts per launch, 5 launches"},
+                "config": "256 four-player opening roots x 10 candidate cards x 2000 rollouts per launch, 5 launches", "roofline": mcs_roofline},
+        "sweep_p10": sweep,
     }
     if world == 1 and not args.no_cpu_baseline:
         import oracle
@@ -521,6 +574,20 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{per_thread * cores} random-vs-random 4-player games ({n} env steps incl. deal and per-step observations) in {dt:.1f} s on {cores} threads, {cpu_model()}; C port of the reference algorithm (oracle/nimmt_oracle.c)"}
+        # the MCS agent's rollout loop (agents/mcts.py:91-154) on the same host cores, same root shape as the GPU number
+        o = obs0[0]
+        board = [[int(c) for c in row if c >= 0] for row in o[0, -24:].reshape(4, 6)]
+        own = [int(c) for c in o[0, :10]]
+        avail = [c for c in range(104) if c not in set(own) | set(sum(board, []))]
+        t0 = time.perf_counter()
+        oracle.bench_mcs(P, board, own, avail, 2000, cores, seed=5)
+        rate = 2000 * cores / (time.perf_counter() - t0)
+        per_thread = max(2000, int(rate * 8 / cores))   # ~8 s of CPU work
+        t0 = time.perf_counter()
+        st = oracle.bench_mcs(P, board, own, avail, per_thread, cores, seed=6)
+        dt = time.perf_counter() - t0
+        line["mcs"]["cpu_baseline"] = {"value": int(st[:, 2].sum()) / dt, "unit": "rollouts/s", "cores": cores, "kind": "port",
+                                       "sample": f"{int(st[:, 2].sum())} reference-law rollouts of a 4-player opening root (determinise + 10 turns, agents/mcts.py:108-154) in {dt:.1f} s on {cores} threads; C port (oracle/nimmt_oracle.c)"}
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
@@ -536,6 +603,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep-log2", type=lambda v: [int(x) for x in v.split(",") if x], default=[20, 24, 28],
+                    help="total games of the ten-player sweep (BASELINE configs[4]), log2, split evenly over the GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         # keep the CPU arm within minutes: one step is ~0.25 s of 8-thread work

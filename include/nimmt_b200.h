@@ -218,8 +218,8 @@ NIMMT_API int nimmt_policy_probs(const int8_t *obs, int64_t num_decisions, const
  *   root_probs float [D][10]      policy at the root (what PUCT uses as prior; log of it is the agent's log_prob)
  * The caller applies the final rule (_choose_action_from_outcomes, agents/mcts.py:156-165) to `stats`.
  * A search is inherently sequential (PUCT reads all earlier outcomes), so one decision is never split over
- * GPUs; shard the D roots instead.  n_mc <= 65535 (the root's outcome histogram counts in 16 bits); larger budgets
- * return NIMMT_E_BADARG. */
+ * GPUs; shard the D roots instead.  With NIMMT_ROOT_PUCT n_mc <= 65535 (the root's outcome histogram, which the
+ * median of _normalize_q is read from, counts in 16 bits); larger budgets return NIMMT_E_BADARG. */
 NIMMT_API int nimmt_policy_rollouts(const nimmt_root *roots, int num_roots, int num_players, const void *weights, int n_mc,
                                     float c_puct, int root_rule, uint64_t seed, int64_t *stats, float *root_probs,
                                     void *stream);

@@ -57,10 +57,12 @@ __global__ void __launch_bounds__(kDealThreads) k_deal(StateView s, uint64_t see
     __shared__ uint8_t values[128];
     __shared__ __align__(16) uint8_t decks[kCards * kDealThreads];
     stage_card_values(values);
-    {   // word k = entry k / 32 of four games = that card id in all four bytes; thread t writes words t, t + 128, ...
-        uint32_t v = (threadIdx.x >> 5) * 0x01010101u;
+    {   // 16-byte chunk c = words 4 c .. 4 c + 3 = entry c / 8 of sixteen games = that card id in every byte; thread t
+        // writes chunks t, t + 128, ... (832 chunks)
+        uint32_t v = (threadIdx.x >> 3) * 0x01010101u;
 #pragma unroll
-        for (int k = 0; k < kCards * 32 / kDealThreads; ++k, v += (kDealThreads / 32) * 0x01010101u) reinterpret_cast<uint32_t*>(decks)[k * kDealThreads + threadIdx.x] = v;
+        for (int c = threadIdx.x; c < kCards * 8; c += kDealThreads, v += (kDealThreads / 8) * 0x01010101u)
+            reinterpret_cast<uint4*>(decks)[c] = make_uint4(v, v, v, v);
     }
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * kDealThreads + threadIdx.x;

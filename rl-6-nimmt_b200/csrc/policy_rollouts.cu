@@ -346,8 +346,10 @@ extern "C" {
 
 int nimmt_policy_rollouts(const nimmt_root* roots, int num_roots, int num_players, const void* weights, int n_mc, float c_puct,
                           int mode, uint64_t seed, int64_t* stats, float* root_probs, void* stream) {
-    // n_mc <= 65535: the root's outcome histogram counts in 16 bits (puct.cuh::RootStats)
-    if (!roots || !weights || !stats || !root_probs || num_roots < 0 || n_mc < 0 || n_mc > 65535 || mode < 0 || mode > 2 ||
+    // PUCT reads the median of all outcomes from a histogram that counts in 16 bits (puct.cuh::RootStats): n_mc <= 65535 there;
+    // the other root rules never read it
+    if (!roots || !weights || !stats || !root_probs || num_roots < 0 || n_mc < 0 || n_mc >= (1 << 24) || mode < 0 || mode > 2 ||
+        (mode == NIMMT_ROOT_PUCT && n_mc > 65535) ||
         num_players < 1 || num_players > kMaxPlayers)
         return NIMMT_E_BADARG;
     if (!aligned16(roots) || !aligned16(weights) || (reinterpret_cast<uintptr_t>(stats) & 7u)) return NIMMT_E_ALIGN;
