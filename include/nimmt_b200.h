@@ -121,6 +121,25 @@ NIMMT_API int nimmt_step(void *state, const uint8_t *actions, int8_t *rewards, u
 NIMMT_API int nimmt_observe(const void *state, void *obs, uint8_t *n_legal, int64_t num_games, int num_players,
                   int include_summaries, int dtype, void *stream);
 
+/* nimmt_step with the FREE ROW CHOICE of the real game, which the reference marks as a TODO (env.py:154-159, ":156 TODO: In the
+ * long term this should be up to the agents"; README.md:11): rows uint8 [B][P] names, for every player, the row (0..3) they
+ * take IF their card is lower than every row's top card; it replaces the lowest-penalty rule of _pick_row_to_replace and is
+ * ignored otherwise.  A value outside 0..3 rejects the game's step exactly like a card that is not in hand (illegal = 1, game
+ * untouched).  With rows[b][p] = the lowest-penalty row this is nimmt_step bit for bit.  Everything else as nimmt_step. */
+NIMMT_API int nimmt_step_choice(void *state, const uint8_t *actions, const uint8_t *rows, int8_t *rewards, uint8_t *done,
+                                uint8_t *illegal, int64_t num_games, int num_players, void *stream);
+
+/* SechsNimmtEnv.step of ONE game, complete, in one launch (env.py:64-77) — the B = 1 drop-in's path.  `cards_host` is a HOST
+ * pointer to the P cards played (read during the call, passed to the kernel by value: no copy is enqueued); NULL = do not step,
+ * only describe the current state (after reset / reset_to, env.py:51,62).  `record` is 512 bytes of device-ACCESSIBLE memory,
+ * 16-byte aligned — typically mapped pinned host memory, so that one stream synchronisation is all the host needs:
+ *     [0, P) rewards int8 | [P] done | [P+1] illegal (the game was left untouched, env.py:68-69) | [16, 16+P) cumulative
+ *     Hornochsen uint8 | [32, 32 + P L) the observations of all seats, int8 [P][L], L = nimmt_obs_len(include_summaries)
+ * `game` selects the game within `state` (0 for a one-game state).  `rows_host` (HOST pointer, P bytes, or NULL): the free
+ * row choice of nimmt_step_choice. */
+NIMMT_API int nimmt_step1(void *state, int64_t game, const uint8_t *cards_host, const uint8_t *rows_host, int num_players,
+                          int include_summaries, void *record, void *stream);
+
 /* Packs per-game flag bytes (the `done` or `illegal` output of nimmt_step: 0 / non-zero) into bits, game b ->
  * bit (b & 31) of bits[b >> 5]; bits has ceil(B / 32) words, unused high bits of the last word are 0.  The
  * reference returns `done` as one Python bool per env.step (env.py:75, 246-249); for a batch whose results go back
@@ -178,6 +197,17 @@ NIMMT_API int nimmt_mc_roots(const void *state, void *available, nimmt_root *roo
  * ascending card order; cards without rollouts never win).  Other seats' bytes of `actions` are untouched. */
 NIMMT_API int nimmt_mc_choose(const void *state, const int64_t *stats, uint8_t *actions, int64_t num_games, int num_players,
                               int seat, void *stream);
+
+/* Tournament._compute_elos (tournament.py:157-164) for B finished games, in order (game b+1 sees the ratings game b left):
+ * multiplayer Elo as the reference's `multi_elo.calc_elo(players, k)` computes it — every pair of players is a two-player
+ * match, K = k / (P - 1), S = 1 / 0.5 / 0 by place, E = 1 / (1 + 10^((R_opp - R_own) / 400)), all seats updated from the
+ * ratings before the game.  (`multi_elo` is third-party and absent from the reference tree: parity unpinned.)
+ *   scores  int32 [B][P]   session results (negative Hornochsen totals, play.py:69-74): higher = better place
+ *   agents  int32 [B][P]   rating slot of every seat, or NULL (seat p = slot p); the seats of one game must be distinct slots
+ *   ratings double [A]     in/out, on the device (Tournament starts every agent at elo_initial = 1600, k = elo_k = 32)
+ *   history double [B][P]  may be NULL; the seat's rating after each game (what Tournament.elos accumulates) */
+NIMMT_API int nimmt_elo_scan(const int32_t *scores, const int32_t *agents, double *ratings, int64_t num_games, int num_players,
+                             double k, double *history, void *stream);
 
 /* ---- Alpha0.5 leaf evaluation (the only dense GEMM on the path; tcgen05 tensor cores) ---- */
 

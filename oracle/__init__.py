@@ -44,6 +44,7 @@ def lib():
         i64p = ctypes.POINTER(ctypes.c_int64)
         L.oracle_card_value.argtypes = [ctypes.c_int]
         L.oracle_replay.argtypes = [ctypes.c_int] * 4 + [i8p, i8p, i8p, i8p, u8p, u8p, i8p, i8p, i16p, i8p]
+        L.oracle_replay_choice.argtypes = [ctypes.c_int] * 4 + [i8p, i8p, i8p, i8p, i8p, u8p, u8p, i8p, i8p, i16p, i8p]
         L.oracle_mcs_rollouts.argtypes = [ctypes.c_int, i32p, i32p, ctypes.c_int, i32p, ctypes.c_int,
                                           ctypes.c_int64, ctypes.c_uint64, ctypes.c_int, i64p]
         L.oracle_bench_env.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_uint64, i64p]
@@ -76,8 +77,9 @@ def deal_from_perm(perm, num_players):
     return hands.astype(np.int8), rows.astype(np.int8)
 
 
-def replay(num_players, rows0, hands0, actions, include_summaries=True, want_obs=True):
-    """Replays games through the C oracle.
+def replay(num_players, rows0, hands0, actions, include_summaries=True, want_obs=True, row_choice=None):
+    """Replays games through the C oracle.  ``row_choice`` (int8 [n,T,P], values 0..3): the optional free-row-choice mode —
+    the row a player takes if their card undercuts every row (env.py:156 TODO); None = the reference's lowest-penalty rule.
 
     rows0 [n,4,6] int8 (-1 padded), hands0 [n,P,10] int8 (-1 padded), actions [n,T,P] int8.
     Returns dict(rewards [n,T,P] i8, done [n,T] u8, illegal [n,T] u8, hands [n,T,P,10] i8,
@@ -96,8 +98,12 @@ def replay(num_players, rows0, hands0, actions, include_summaries=True, want_obs
         hands=np.zeros((n, T, P, 10), np.int8), boards=np.zeros((n, T, 4, 6), np.int8),
         scores=np.zeros((n, T, P), np.int16), obs=np.zeros((n, T, P, L_obs), np.int8) if want_obs else None,
     )
-    rc = lib().oracle_replay(
+    if row_choice is not None:
+        row_choice = np.ascontiguousarray(row_choice, dtype=np.int8)
+        assert row_choice.shape == (n, T, P)
+    rc = lib().oracle_replay_choice(
         P, n, T, int(include_summaries), _p(rows0, ctypes.c_int8), _p(hands0, ctypes.c_int8), _p(actions, ctypes.c_int8),
+        _p(row_choice, ctypes.c_int8) if row_choice is not None else None,
         _p(out["rewards"], ctypes.c_int8), _p(out["done"], ctypes.c_uint8), _p(out["illegal"], ctypes.c_uint8),
         _p(out["hands"], ctypes.c_int8), _p(out["boards"], ctypes.c_int8), _p(out["scores"], ctypes.c_int16),
         _p(out["obs"], ctypes.c_int8) if want_obs else None,

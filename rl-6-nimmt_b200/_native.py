@@ -42,6 +42,8 @@ SIGNATURES = {
     "nimmt_deal_from_perm": (_int, [_vp, _vp, _i64, _int, _vp]),
     "nimmt_reset_to": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp]),
     "nimmt_step": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
+    "nimmt_step1": (_int, [_vp, _i64, _vp, _vp, _int, _int, _vp, _vp]),
+    "nimmt_step_choice": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
     "nimmt_pack_flags": (_int, [_vp, _vp, _i64, _vp]),
     "nimmt_observe": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
     "nimmt_scores": (_int, [_vp, _vp, _i64, _int, _vp]),
@@ -50,6 +52,7 @@ SIGNATURES = {
     "nimmt_mcs_rollouts": (_int, [_vp, _int, _int, _i64, _u64, _int, _int, _vp, _vp]),
     "nimmt_mc_roots": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
     "nimmt_mc_choose": (_int, [_vp, _vp, _vp, _i64, _int, _int, _vp]),
+    "nimmt_elo_scan": (_int, [_vp, _vp, _vp, _i64, _int, ctypes.c_double, _vp, _vp]),
     "nimmt_policy_weights_bytes": (ctypes.c_size_t, []),
     "nimmt_policy_pack_weights": (_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_float, _vp]),
     "nimmt_policy_probs": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),

@@ -136,6 +136,51 @@ static void launch_observe(const StateView& s, void* obs, uint8_t* n_legal, int6
         k_observe<P, T, false><<<blocks_for(B, TPB), TPB, 0, st>>>(s, reinterpret_cast<T*>(obs), n_legal);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_step1 — the whole env.step of ONE game in one launch, for the B = 1 drop-in (SechsNimmtEnv, env.py:64-77): check and
+// play the cards (passed by value: no host-to-device copy), then rewards, done, illegal, the cumulative scores and the
+// observations of all P seats go out as ONE 512-byte record written with a single coalesced 16-byte store per lane — into
+// mapped pinned host memory, so the host needs one stream synchronisation and no copy at all.  With do_step = 0 the
+// record describes the current state (reset / reset_to).
+//   record: [0, P) rewards int8 | [P] done | [P + 1] illegal | [16, 16 + P) scores uint8 | [32, 32 + P L) observations int8 [P][L]
+// ------------------------------------------------------------------------------------------
+struct Step1Cards {
+    uint8_t card[16];
+    uint8_t row[16];   // free-row-choice mode: the row each player takes on an undercut
+};
+
+template <int P>
+__global__ void __launch_bounds__(32) k_step1(StateView s, int64_t g, Step1Cards cards, int do_step, int choose_rows, int summaries, uint4* __restrict__ out) {
+    __shared__ uint8_t values[128];
+    __shared__ __align__(16) uint8_t rec[512];
+    __shared__ GameRec<P> gm;
+    stage_card_values(values);
+    reinterpret_cast<uint4*>(rec)[threadIdx.x] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        load_game<P>(s, g, gm);
+        bool legal = true;
+        if (do_step) {
+            int act[P], pen[P], choice[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) { act[p] = cards.card[p]; choice[p] = cards.row[p]; }
+            legal = step_game<P>(gm, act, values, pen, choose_rows ? choice : nullptr);
+            if (legal) store_step<P>(s, g, gm);
+#pragma unroll
+            for (int p = 0; p < P; ++p) rec[p] = (uint8_t)(legal ? -pen[p] : 0);
+        }
+        rec[P] = game_done<P>(gm);
+        rec[P + 1] = !legal;
+#pragma unroll
+        for (int p = 0; p < P; ++p) rec[16 + p] = (uint8_t)rec_score(gm.hand[p]);
+    }
+    __syncwarp();
+    const int L = summaries ? 47 : 35;
+    if (threadIdx.x < P) fill_observation<P>(gm, threadIdx.x, reinterpret_cast<int8_t*>(rec) + 32 + threadIdx.x * L, summaries != 0);
+    __syncwarp();
+    out[threadIdx.x] = reinterpret_cast<const uint4*>(rec)[threadIdx.x];
+}
+
 }  // namespace nimmt
 
 using namespace nimmt;
@@ -156,6 +201,22 @@ int nimmt_observe(const void* state, void* obs, uint8_t* n_legal, int64_t B, int
         case NIMMT_DT_F32: launch_observe<P, float>(s, obs, n_legal, B, include_summaries, st); break;
         default: launch_observe<P, int64_t>(s, obs, n_legal, B, include_summaries, st); break;
     });
+    return check_launch();
+}
+
+int nimmt_step1(void* state, int64_t game, const uint8_t* cards_host, const uint8_t* rows_host, int num_players, int include_summaries, void* record,
+                void* stream) {
+    if (int rc = check_common(state, game + 1, num_players)) return rc;
+    if (!record || game < 0) return NIMMT_E_BADARG;
+    if (!aligned16(record)) return NIMMT_E_ALIGN;
+    Step1Cards c;
+    for (int p = 0; p < 16; ++p) {
+        c.card[p] = cards_host && p < num_players ? cards_host[p] : (uint8_t)255;
+        c.row[p] = rows_host && p < num_players ? rows_host[p] : (uint8_t)0;
+    }
+    StateView s(state, game + 1, num_players);
+    NIMMT_DISPATCH_P(num_players, k_step1<P><<<1, 32, 0, (cudaStream_t)stream>>>(s, game, c, cards_host != nullptr, rows_host != nullptr, include_summaries,
+                                                                                 static_cast<uint4*>(record)));
     return check_launch();
 }
 

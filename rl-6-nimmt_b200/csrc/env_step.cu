@@ -15,7 +15,7 @@ template <int P, bool kRandom>
 __global__ void __launch_bounds__(kStepThreads)
 k_step(StateView s, const uint8_t* __restrict__ actions_in, uint8_t* __restrict__ actions_out, int8_t* __restrict__ rewards,
        uint8_t* __restrict__ done, uint8_t* __restrict__ illegal, uint64_t seed, uint32_t turn, uint64_t game0,
-       int64_t first_game) {
+       int64_t first_game, const uint8_t* __restrict__ rows = nullptr) {
     __shared__ uint8_t values[128];
     const int64_t g_raw = first_game + (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
     const bool valid = g_raw < s.B;
@@ -37,8 +37,9 @@ k_step(StateView s, const uint8_t* __restrict__ actions_in, uint8_t* __restrict_
         if (actions_out) store_bytes<P>(actions_out, g, act);
     }
 
-    int penalty[P];
-    const bool legal = step_game<P>(gm, act, values, penalty);
+    int penalty[P], choice[P];
+    if (rows) load_bytes<P>(rows, g, choice);   // free-row-choice mode (env.py:156 TODO)
+    const bool legal = step_game<P>(gm, act, values, penalty, rows ? choice : nullptr);
     if (legal) store_step<P>(s, g, gm);
 
     int rew[P];
@@ -67,10 +68,10 @@ k_step(StateView s, const uint8_t* __restrict__ actions_in, uint8_t* __restrict_
 // Tuning knobs (profiles/tools/build_variants.sh builds and times the alternatives): consumer warps = tiles per group, and
 // pipeline stages, for small (P <= 5) and large tables.
 #ifndef NIMMT_STEP_WARPS_SMALL
-#define NIMMT_STEP_WARPS_SMALL 4
+#define NIMMT_STEP_WARPS_SMALL 8
 #endif
 #ifndef NIMMT_STEP_WARPS_LARGE
-#define NIMMT_STEP_WARPS_LARGE 2
+#define NIMMT_STEP_WARPS_LARGE 4
 #endif
 #ifndef NIMMT_STEP_STAGES_SMALL
 #define NIMMT_STEP_STAGES_SMALL 3
@@ -84,22 +85,24 @@ struct StepShape {
     static constexpr int kStages = P <= 5 ? NIMMT_STEP_STAGES_SMALL : NIMMT_STEP_STAGES_LARGE;
 };
 
-template <int P, int W>
+template <int P, int W, bool kChoice = false>
 struct StageLayout {
     using L = TileLayout<P>;
     static constexpr int kTiles = 0;                                          // W tile records
     static constexpr int kActions = W * L::kTileBytes;                        // W x 32 x P action bytes
-    static constexpr int kBytes = kActions + W * L::kActBytes;
+    static constexpr int kChoices = kActions + W * L::kActBytes;              // kChoice: W x 32 x P row-choice bytes
+    static constexpr int kBytes = kChoices + (kChoice ? W * L::kActBytes : 0);
     static constexpr int kStride = (kBytes + 127) / 128 * 128;
 };
 
-template <int P, bool kRandom>
+template <int P, bool kRandom, bool kChoice = false>
 __global__ void __launch_bounds__((StepShape<P>::kWarps + 1) * 32)
 k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restrict__ actions_out, int8_t* __restrict__ rewards,
-             uint8_t* __restrict__ done, uint8_t* __restrict__ illegal, int num_tiles, uint64_t seed, uint32_t turn, uint64_t game0) {
+             uint8_t* __restrict__ done, uint8_t* __restrict__ illegal, int num_tiles, uint64_t seed, uint32_t turn, uint64_t game0,
+             const uint8_t* __restrict__ rows = nullptr) {
     constexpr int W = StepShape<P>::kWarps, S = StepShape<P>::kStages;
     using L = TileLayout<P>;
-    using G = StageLayout<P, W>;
+    using G = StageLayout<P, W, kChoice>;
     extern __shared__ __align__(128) uint8_t stage_smem[];   // S x G::kStride
     __shared__ uint64_t full[S], computed[S];
     __shared__ uint8_t values5[128];
@@ -125,9 +128,10 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
             const int first = group * W;
             const uint32_t n = (uint32_t)min(W, num_tiles - first);       // the last group may be short
             const uint32_t buf = stage_a + (uint32_t)stage * G::kStride, bar = full_a + 8u * (uint32_t)stage;
-            mbar_arrive_expect_tx_a(bar, n * (uint32_t)(kRandom ? L::kTileBytes : L::kTileBytes + L::kActBytes));
+            mbar_arrive_expect_tx_a(bar, n * (uint32_t)(L::kTileBytes + (kRandom ? 0 : L::kActBytes) + (kChoice ? L::kActBytes : 0)));
             bulk_load_a(buf, s.tile_ptr(first), n * L::kTileBytes, bar);
             if constexpr (!kRandom) bulk_load_a(buf + G::kActions, actions + (int64_t)first * L::kActBytes, n * L::kActBytes, bar);
+            if constexpr (kChoice) bulk_load_a(buf + G::kChoices, rows + (int64_t)first * L::kActBytes, n * L::kActBytes, bar);
         };
         const bool issuer = elect_one() != 0u;
         {
@@ -169,10 +173,11 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
         mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
         if (group * W + warp < num_tiles) {
             const int64_t g0 = (int64_t)group * (W * kTileGames);           // warp-uniform: lives on the uniform datapath
-            step_lane<P, kRandom>(tile, stage_smem + stage * G::kStride + G::kActions + warp * L::kActBytes, lane, values5, kw, ku,
-                                  reinterpret_cast<uint8_t*>(rewards) + g0 * P + lane_game * P, done + g0 + lane_game,
-                                  illegal ? illegal + g0 + lane_game : nullptr, actions_out ? actions_out + g0 * P + lane_game * P : nullptr, seed,
-                                  game0 + (uint64_t)g0 + lane_game, turn);
+            step_lane<P, kRandom, kChoice>(tile, stage_smem + stage * G::kStride + G::kActions + warp * L::kActBytes, lane, values5, kw, ku,
+                                           reinterpret_cast<uint8_t*>(rewards) + g0 * P + lane_game * P, done + g0 + lane_game,
+                                           illegal ? illegal + g0 + lane_game : nullptr, actions_out ? actions_out + g0 * P + lane_game * P : nullptr,
+                                           seed, game0 + (uint64_t)g0 + lane_game, turn,
+                                           stage_smem + stage * G::kStride + G::kChoices + warp * L::kActBytes);
             fence_async_smem();   // make this lane's shared-memory writes visible to the TMA engine
         }
         __syncwarp();
@@ -182,26 +187,26 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
 }
 
 // kRandom = false: actions is the tape to play; true: actions (may be NULL) receives the cards drawn in the kernel.
-template <int P, bool kRandom>
+template <int P, bool kRandom, bool kChoice = false>
 static int launch_step(const StateView& s, uint8_t* actions, int8_t* rewards, uint8_t* done, uint8_t* illegal, uint64_t seed, uint32_t turn,
-                       uint64_t game0, cudaStream_t st) {
+                       uint64_t game0, cudaStream_t st, const uint8_t* rows = nullptr) {
     constexpr int W = StepShape<P>::kWarps, S = StepShape<P>::kStages;
-    constexpr int kSmem = S * StageLayout<P, W>::kStride;
+    constexpr int kSmem = S * StageLayout<P, W, kChoice>::kStride;
     constexpr int kThreads = (W + 1) * 32;
     const int64_t num_tiles = s.B / kTileGames;
     if (num_tiles > 0) {
         static int occ_cache[kMaxDevices];   // per device: the shared-memory opt-in and the occupancy are device properties
-        const int blocks_per_sm = blocks_per_sm_cached(k_step_tiles<P, kRandom>, kThreads, kSmem, occ_cache);
+        const int blocks_per_sm = blocks_per_sm_cached(k_step_tiles<P, kRandom, kChoice>, kThreads, kSmem, occ_cache);
         const int num_sms = device_sms(current_device());
         // persistent grid: one resident wave; block b walks groups b, b + #blocks, ...
         const int64_t groups = (num_tiles + W - 1) / W;
         const unsigned blocks = (unsigned)min(groups, (int64_t)num_sms * blocks_per_sm);
-        k_step_tiles<P, kRandom><<<blocks, kThreads, kSmem, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, (int)num_tiles, seed,
-                                                                 turn, game0);
+        k_step_tiles<P, kRandom, kChoice><<<blocks, kThreads, kSmem, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, (int)num_tiles,
+                                                                          seed, turn, game0, rows);
     }
     const int64_t tail0 = num_tiles * kTileGames;
     if (tail0 < s.B)   // ragged tail (< 32 games): plain loads
-        k_step<P, kRandom><<<1, kStepThreads, 0, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, seed, turn, game0, tail0);
+        k_step<P, kRandom><<<1, kStepThreads, 0, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, seed, turn, game0, tail0, rows);
     return 0;
 }
 
@@ -243,6 +248,17 @@ int nimmt_step(void* state, const uint8_t* actions, int8_t* rewards, uint8_t* do
     if (B == 0) return NIMMT_OK;
     StateView s(state, B, num_players);
     NIMMT_DISPATCH_P(num_players, (launch_step<P, false>(s, const_cast<uint8_t*>(actions), rewards, done, illegal, 0, 0, 0, (cudaStream_t)stream)));
+    return check_launch();
+}
+
+int nimmt_step_choice(void* state, const uint8_t* actions, const uint8_t* rows, int8_t* rewards, uint8_t* done, uint8_t* illegal, int64_t B,
+                      int num_players, void* stream) {
+    if (int rc = check_common(state, B, num_players)) return rc;
+    if (!actions || !rows || !rewards || !done) return NIMMT_E_BADARG;
+    if (!aligned16(actions) || !aligned16(rows) || !aligned16(rewards) || !aligned16(done) || (illegal && !aligned16(illegal))) return NIMMT_E_ALIGN;
+    if (B == 0) return NIMMT_OK;
+    StateView s(state, B, num_players);
+    NIMMT_DISPATCH_P(num_players, (launch_step<P, false, true>(s, const_cast<uint8_t*>(actions), rewards, done, illegal, 0, 0, 0, (cudaStream_t)stream, rows)));
     return check_launch();
 }
 

@@ -267,14 +267,17 @@ struct RowKeys {
     //                                      holds five cards the player takes those five
     // In both take cases the penalty is the row's sum BEFORE the append and the row restarts with
     // the played card alone.
-    NIMMT_HD int place(int card, int value, int& row, uint32_t& keep_len) {
+    // `choice` >= 0: the free-row-choice mode (env.py:156 TODO) — on an undercut the player takes row `choice` instead of the
+    // cheapest one.
+    NIMMT_HD int place(int card, int value, int& row, uint32_t& keep_len, int choice = -1) {
         const int ck = card << 10;
         // largest w below ck == smallest positive ck - w; rows above the card wrap to huge unsigned values
         const uint32_t d0 = (uint32_t)(ck - w[0]), d1 = (uint32_t)(ck - w[1]);
         const uint32_t d2 = (uint32_t)(ck - w[2]), d3 = (uint32_t)(ck - w[3]);
         const uint32_t dmin = umin32(umin32(d0, d1), umin32(d2, d3));
         const int best = ck - (int)dmin;
-        const int cheapest = imin(imin(u[0], u[1]), imin(u[2], u[3]));
+        int cheapest = imin(imin(u[0], u[1]), imin(u[2], u[3]));
+        if (choice >= 0) cheapest = choice == 0 ? u[0] : choice == 1 ? u[1] : choice == 2 ? u[2] : u[3];
         const bool under = dmin > (uint32_t)ck;   // card below every top
         const int r = (under ? cheapest : best) & 3;
         const uint32_t len = ((uint32_t)best >> 2) & 7u;  // garbage when under; take is true then
@@ -346,8 +349,9 @@ constexpr uint32_t kSumField = 0x3E0u, kLenField = 0x1Cu;
 
 NIMMT_HD uint32_t key_u_from_w(uint32_t w) { return w & (kSumField | 3u); }
 
-template <int STRIDE = 1>
-NIMMT_HD uint32_t place_v3(uint32_t* w, uint32_t* u, uint32_t key, const uint8_t* values5, uint32_t& row, uint32_t& keep4) {
+// kChoice: the free-row-choice mode (env.py:156 TODO, README.md:11) — on an undercut the row is `choice` (0..3), not the cheapest.
+template <int STRIDE = 1, bool kChoice = false>
+NIMMT_HD uint32_t place_v3(uint32_t* w, uint32_t* u, uint32_t key, const uint8_t* values5, uint32_t& row, uint32_t& keep4, uint32_t choice = 0) {
     uint4 W, U;
     if constexpr (STRIDE == 1) {
         W = *reinterpret_cast<const uint4*>(w);
@@ -357,7 +361,7 @@ NIMMT_HD uint32_t place_v3(uint32_t* w, uint32_t* u, uint32_t key, const uint8_t
         U = make_uint4(u[0], u[STRIDE], u[2 * STRIDE], u[3 * STRIDE]);
     }
     const uint32_t dmin = umin32(umin32(key - W.x, key - W.y), umin32(key - W.z, key - W.w));   // rows above the card wrap to huge values
-    const uint32_t cheapest = umin32(umin32(U.x, U.y), umin32(U.z, U.w));
+    const uint32_t cheapest = kChoice ? u[choice * STRIDE] : umin32(umin32(U.x, U.y), umin32(U.z, U.w));
     const bool under = dmin > key;                          // card below every top (env.py:143)
     const uint32_t best = key - dmin;                       // == W of the row with the largest top below the card
     const uint32_t sel = under ? cheapest : best;
@@ -414,10 +418,10 @@ struct Board {
         q2 = (uint64_t)slot[4] | ((uint64_t)metas << 32);
     }
 
-    NIMMT_HD int place(int card, int value) {
+    NIMMT_HD int place(int card, int value, int choice = -1) {
         int r;
         uint32_t keep_len;
-        const int penalty = k.place(card, value, r, keep_len);
+        const int penalty = k.place(card, value, r, keep_len, choice);
         // write the one slot the card lands in; slots at index >= len keep whatever they held
         // (they are unspecified in the stored record: k_step_smem writes a single byte too)
         const uint32_t shift = 8u * keep_len;

@@ -69,6 +69,44 @@ k_mc_choose(StateView s, const long long* __restrict__ stats, uint8_t* __restric
     actions[g * P + seat] = n > 0 ? (uint8_t)rec_select(rec, (uint32_t)best) : (uint8_t)255;
 }
 
+// ------------------------------------------------------------------------------------------
+// k_elo_scan — Tournament._compute_elos (tournament.py:157-164) for B finished games IN ORDER: the multiplayer Elo of the
+// `multi_elo` package the reference calls (`calc_elo(players, k)`), i.e. every pair of players of a game is a two-player match,
+//     K = k / (n - 1),   S_ij = 1 if place_i < place_j, 1/2 if equal, 0 otherwise,   E_ij = 1 / (1 + 10^((R_j - R_i) / 400)),
+//     R_i <- R_i + K * sum_{j != i} (S_ij - E_ij)          (all players of the game updated from the ratings before the game)
+// with place = the tie-averaged rank by score (tournament.py:240-247; only its order matters here).  Elo is sequential by
+// nature — game b+1 sees the ratings left by game b — so one warp walks the games; lane p is seat p of the current game.
+// `multi_elo` is a third-party dependency absent from the reference tree and from this image: the formula above is its
+// published algorithm (no rounding of the terms), parity is UNPINNED and says so in DESIGN.md.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_elo_scan(const int* __restrict__ scores, const int* __restrict__ agents, double* __restrict__ ratings, int64_t B, int P, double k,
+           double* __restrict__ history) {
+    const int lane = threadIdx.x;
+    const double K = k / (double)(P > 1 ? P - 1 : 1);
+    for (int64_t b = 0; b < B; ++b) {
+        const bool live = lane < P;
+        const int me = live ? (agents ? agents[b * P + lane] : lane) : 0;
+        const int score = live ? scores[b * P + lane] : 0;
+        const double r = live ? ratings[me] : 0.0;
+        double delta = 0.0;
+        for (int j = 0; j < P; ++j) {
+            const int sj = __shfl_sync(0xffffffffu, score, j);
+            const double rj = __shfl_sync(0xffffffffu, r, j);
+            if (live && j != lane) {
+                const double s = score > sj ? 1.0 : (score == sj ? 0.5 : 0.0);   // higher score = better place (scores are <= 0)
+                delta += s - 1.0 / (1.0 + pow(10.0, (rj - r) / 400.0));
+            }
+        }
+        __syncwarp();
+        if (live) {
+            ratings[me] = r + K * delta;
+            if (history) history[b * P + lane] = r + K * delta;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace nimmt
 
 using namespace nimmt;
@@ -94,6 +132,14 @@ int nimmt_mc_choose(const void* state, const int64_t* stats, uint8_t* actions, i
     StateView s(const_cast<void*>(state), B, num_players);
     NIMMT_DISPATCH_P(num_players, k_mc_choose<P><<<blocks_for(B, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
                                       s, reinterpret_cast<const long long*>(stats), actions, seat));
+    return check_launch();
+}
+
+int nimmt_elo_scan(const int32_t* scores, const int32_t* agents, double* ratings, int64_t num_games, int num_players, double k,
+                   double* history, void* stream) {
+    if (!scores || !ratings || num_games < 0 || num_players < 1 || num_players > 32 || !(k >= 0.0)) return NIMMT_E_BADARG;
+    if (num_games == 0) return NIMMT_OK;
+    k_elo_scan<<<1, 32, 0, (cudaStream_t)stream>>>(scores, agents, ratings, num_games, num_players, k, history);
     return check_launch();
 }
 

@@ -77,8 +77,9 @@ template <> struct PenaltyPack<5> { using type = uint32_t; };
 
 // SechsNimmtEnv._play_cards (env.py:120-136) on a board: the cards are resolved in ascending order, penalty[p]
 // receives the bull heads player p takes this step (reward = -penalty, env.py:169).
+// `choice` (may be NULL): the free-row-choice mode — choice[p] is the row player p takes if their card undercuts every row.
 template <int P>
-NIMMT_HD void play_cards(Board& board, const int (&act)[P], const uint8_t* values, int (&penalty)[P]) {
+NIMMT_HD void play_cards(Board& board, const int (&act)[P], const uint8_t* values, int (&penalty)[P], const int* choice = nullptr) {
     // sorted((card, player)) ascending by card (env.py:124-125)
     int keys[P];
 #pragma unroll
@@ -89,7 +90,12 @@ NIMMT_HD void play_cards(Board& board, const int (&act)[P], const uint8_t* value
 #pragma unroll
     for (int i = 0; i < P; ++i) {
         const int card = keys[i] >> 4, player = keys[i] & 15;
-        const int pen = board.place(card, values[card]);  // env.py:126-134
+        int chosen = -1;
+        if (choice) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) chosen = p == player ? choice[p] : chosen;   // static indices: no local memory
+        }
+        const int pen = board.place(card, values[card], chosen);  // env.py:126-134
         packed += (typename PenaltyPack<P>::type)pen << (6 * player);
     }
 #pragma unroll
@@ -103,7 +109,7 @@ NIMMT_HD void play_cards(Board& board, const int (&act)[P], const uint8_t* value
 // Returns false — and leaves the game untouched — if any card is not in its owner's hand
 // (env.py:68-69: every move is checked before anything is mutated).
 template <int P>
-NIMMT_HD bool step_game(Game<P>& g, const int (&act)[P], const uint8_t* values, int (&penalty)[P]) {
+NIMMT_HD bool step_game(Game<P>& g, const int (&act)[P], const uint8_t* values, int (&penalty)[P], const int* choice = nullptr) {
     // env.py:68-69 + :131 — every card is checked (and tentatively removed) before anything is committed
     uint4 hand[P];
     bool legal = true;
@@ -111,10 +117,11 @@ NIMMT_HD bool step_game(Game<P>& g, const int (&act)[P], const uint8_t* values, 
     for (int p = 0; p < P; ++p) {
         hand[p] = g.hand[p];
         legal = mask_take(hand[p], (uint32_t)act[p], true) && legal;
+        if (choice) legal = legal && (uint32_t)choice[p] < (uint32_t)kRows;
         penalty[p] = 0;
     }
     if (!legal) return false;
-    play_cards<P>(g.board, act, values, penalty);
+    play_cards<P>(g.board, act, values, penalty, choice);
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         hand[p].w += (uint32_t)penalty[p] << kScoreShift;     // env.py:167
@@ -125,16 +132,17 @@ NIMMT_HD bool step_game(Game<P>& g, const int (&act)[P], const uint8_t* values, 
 
 // The same step on the stored form: a played card sets its slot's bit, a take adds to the score field.
 template <int P>
-NIMMT_HD bool step_game(GameRec<P>& g, const int (&act)[P], const uint8_t* values, int (&penalty)[P]) {
+NIMMT_HD bool step_game(GameRec<P>& g, const int (&act)[P], const uint8_t* values, int (&penalty)[P], const int* choice = nullptr) {
     uint32_t meta[P];
     bool legal = true;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         legal = rec_take(g.hand[p], (uint32_t)act[p], meta[p]) && legal;
+        if (choice) legal = legal && (uint32_t)choice[p] < (uint32_t)kRows;
         penalty[p] = 0;
     }
     if (!legal) return false;
-    play_cards<P>(g.board, act, values, penalty);
+    play_cards<P>(g.board, act, values, penalty, choice);
 #pragma unroll
     for (int p = 0; p < P; ++p) g.hand[p].meta = meta[p] + ((uint32_t)penalty[p] << kRecScoreShift);   // env.py:167
     return true;
@@ -248,6 +256,25 @@ NIMMT_HD void set_dealt_hand(GameRec<P>& g, int p, int (&cards)[kHand]) {
 #pragma unroll
     for (int i = 0; i < kHand; ++i) c[i] = (uint32_t)cards[i];
     g.hand[p] = rec_from_sorted(c, kHand, 0u);
+}
+
+// SechsNimmtEnv._create_agent_state + _create_game_state for one seat (env.py:186-212), one int8 per entry:
+// [own hand ascending, -1 padded (10) | P | cards per row (4) top cards (4) bull heads per row (4) — if summaries | board 4 x 6, -1 padded].
+template <int P>
+NIMMT_HD void fill_observation(const GameRec<P>& g, int p, int8_t* o, bool summaries) {
+    int n = 0;
+    for (int i = 0; i < kHand; ++i)
+        if (!rec_slot_empty(g.hand[p], i)) o[n++] = (int8_t)rec_card(g.hand[p], i);
+    for (; n < kHand; ++n) o[n] = -1;
+    o[n++] = (int8_t)P;
+    if (summaries) {
+        for (int r = 0; r < kRows; ++r) o[n + r] = (int8_t)g.board.k.len(r);
+        for (int r = 0; r < kRows; ++r) o[n + 4 + r] = (int8_t)g.board.k.top(r);
+        for (int r = 0; r < kRows; ++r) o[n + 8 + r] = (int8_t)g.board.k.sum(r);
+        n += 12;
+    }
+    for (int r = 0; r < kRows; ++r)
+        for (int i = 0; i < 6; ++i) o[n + r * 6 + i] = i < g.board.k.len(r) ? (int8_t)((g.board.cards[r] >> (8 * i)) & 0xFF) : (int8_t)-1;
 }
 
 // DrunkHamster.forward (agents/random.py:8-10): a uniform card of each non-empty hand.

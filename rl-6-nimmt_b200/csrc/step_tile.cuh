@@ -22,10 +22,12 @@ struct TileLayout {
 //   acts     the tile's action bytes in shared memory (kRandom: unused)
 //   keys_w/u this lane's row keys (game.cuh::place_v3), 16-byte aligned
 // Returns the game's rewards packed one byte per player (P <= 4: one word; larger P: stored through `rew_out`).
-template <int P, bool kRandom>
+//   kChoice  free-row-choice mode: `rows` holds, like `acts`, one byte per (game, player) — the row that player takes if their
+//            card undercuts every row (0..3; anything else rejects the step like an illegal card)
+template <int P, bool kRandom, bool kChoice = false>
 NIMMT_HD void step_lane(uint8_t* tile, const uint8_t* acts, int lane, const uint8_t* values5, uint32_t* keys_w, uint32_t* keys_u,
                                           uint8_t* rew_out, uint8_t* done_out, uint8_t* illegal_out, uint8_t* act_out, uint64_t seed,
-                                          uint64_t game_id, uint32_t turn) {
+                                          uint64_t game_id, uint32_t turn, const uint8_t* rows = nullptr) {
     using L = TileLayout<P>;
     const uint2* cards0 = reinterpret_cast<const uint2*>(tile) + lane;              // + p * kTileGames
     uint32_t* meta0 = reinterpret_cast<uint32_t*>(tile + L::kMeta) + lane;           // + p * kTileGames
@@ -73,6 +75,12 @@ NIMMT_HD void step_lane(uint8_t* tile, const uint8_t* acts, int lane, const uint
         }
         // rec_slot_bit is exact for ids < 128 (104..127 match no stored card; 127 only never-dealt slots, which are marked empty)
         legal = legal && any < 128u;
+        if constexpr (kChoice) {
+            uint32_t all = 0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) all |= rows[lane * P + p];
+            legal = legal && all < (uint32_t)kRows;
+        }
     }
 
     uint32_t gain[P];                                    // score words before - after: the top byte is -(bull heads taken) in two's complement
@@ -107,7 +115,9 @@ NIMMT_HD void step_lane(uint8_t* tile, const uint8_t* acts, int lane, const uint
         for (int i = 0; i < P; ++i) {
             const uint32_t key = (uint32_t)keys[i];
             uint32_t row, keep4;
-            const uint32_t pen5 = place_v3(keys_w, keys_u, key, values5, row, keep4);   // env.py:126-134
+            uint32_t choice = 0;
+            if constexpr (kChoice) choice = rows[lane * P + ((key >> 6) & 15u)];          // the row this card's player named
+            const uint32_t pen5 = place_v3<1, kChoice>(keys_w, keys_u, key, values5, row, keep4, choice);   // env.py:126-134
             rec[keep4 + row] = (uint8_t)(key >> 10);                                      // the one byte of the record a placement changes
             // env.py:167-169: the player of this card takes pen bull heads — added to its score field where the word lives,
             // in shared memory (the player is data: a register array would need a select per player)

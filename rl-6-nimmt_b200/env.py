@@ -139,8 +139,12 @@ class BatchedSechsNimmtEnv:
         self.turn = 0
         return self
 
-    def step(self, actions, check=False):
+    def step(self, actions, check=False, rows=None):
         """SechsNimmtEnv.step (env.py:64-77) without the observation rebuild.
+
+        ``rows`` (uint8 [B,P], optional): the free row choice of the real game, which the reference leaves as a TODO
+        (env.py:156, README.md:11) — the row (0..3) each player takes IF their card undercuts every row, instead of the
+        lowest-penalty rule.  None = the reference's rule.
 
         actions: uint8 [B,P] device tensor.  Returns (rewards int8 [B,P], done uint8 [B]) — views of
         buffers owned by the env, overwritten by the next step.  ``self.illegal`` flags games whose
@@ -150,8 +154,14 @@ class BatchedSechsNimmtEnv:
         assert actions.shape == (self.num_games, self.num_players) and actions.dtype == torch.uint8 and actions.is_cuda
         actions = actions.contiguous()
         with torch.cuda.device(self.device):
-            N.check(self.lib.nimmt_step(N.ptr(self.state), N.ptr(actions), N.ptr(self.rewards), N.ptr(self.done),
-                                        N.ptr(self.illegal), self.num_games, self.num_players, self._stream()), "nimmt_step")
+            if rows is None:
+                N.check(self.lib.nimmt_step(N.ptr(self.state), N.ptr(actions), N.ptr(self.rewards), N.ptr(self.done),
+                                            N.ptr(self.illegal), self.num_games, self.num_players, self._stream()), "nimmt_step")
+            else:
+                assert rows.shape == actions.shape and rows.dtype == torch.uint8 and rows.is_cuda
+                rows = rows.contiguous()
+                N.check(self.lib.nimmt_step_choice(N.ptr(self.state), N.ptr(actions), N.ptr(rows), N.ptr(self.rewards), N.ptr(self.done),
+                                                   N.ptr(self.illegal), self.num_games, self.num_players, self._stream()), "nimmt_step_choice")
         self.turn += 1
         if check and bool(self.illegal.any()):
             bad = int(torch.nonzero(self.illegal)[0])
@@ -243,7 +253,7 @@ class SechsNimmtEnv:
     metadata = {"render.modes": ["human"]}
 
     def __init__(self, num_players, num_rows=4, num_cards=104, threshold=6, include_summaries=True, player_names=None,
-                 verbose=True, device=None):
+                 verbose=True, device=None, row_choice="lowest"):
         assert num_players > 0
         assert num_rows > 0
         assert num_cards >= 10 * num_players + num_rows
@@ -261,7 +271,12 @@ class SechsNimmtEnv:
         self.verbose = verbose
         self._engine = None
         self._device = device
+        # "lowest": the reference's rule (env.py:154-159).  "agent": the real game's free choice, the reference's TODO
+        # (env.py:156) — step(action, rows=[...]) names the row each player takes if their card undercuts every row.
+        assert row_choice in ("lowest", "agent")
+        self._row_choice = row_choice
         self._cache = None  # (obs int64 [P,L] numpy, scores int32 [P]) of the current state
+        self._record = None  # 512 bytes of mapped pinned host memory: what nimmt_step1 reports about the game
 
     # engine is created lazily: agents/base.py:11-12 builds a throw-away env just to read the spaces
     def _eng(self):
@@ -272,12 +287,36 @@ class SechsNimmtEnv:
             self._engine.reset_to(board, -np.ones((1, self._num_players, HAND_SIZE), np.int8), check=False)
         return self._engine
 
+    def _launch1(self, cards=None, rows=None):
+        """One kernel for the whole call (nimmt_step1): with ``cards`` the step itself, always the rewards / done / illegal /
+        scores / every seat's observation of the resulting state, written straight into pinned host memory; one stream
+        synchronisation, no copies.  Returns the record as a numpy view (valid until the next call)."""
+        eng = self._eng()
+        if self._record is None:
+            self._record = torch.zeros(512, dtype=torch.uint8).pin_memory()
+            self._record_np = self._record.numpy()
+            self._cards = np.zeros(16, np.uint8)
+            self._rows = np.zeros(16, np.uint8)
+        ptr = rptr = None
+        if cards is not None:
+            self._cards[: self._num_players] = cards
+            ptr = self._cards.ctypes.data
+        if rows is not None:
+            self._rows[: self._num_players] = rows
+            rptr = self._rows.ctypes.data
+        with torch.cuda.device(eng.device):
+            stream = torch.cuda.current_stream(eng.device)
+            N.check(eng.lib.nimmt_step1(N.ptr(eng.state), 0, ptr, rptr, self._num_players, int(self._include_summaries),
+                                        self._record.data_ptr(), stream.cuda_stream), "nimmt_step1")
+            stream.synchronize()
+        rec = self._record_np
+        P, L = self._num_players, eng.obs_len
+        self._cache = (rec[32:32 + P * L].view(np.int8).reshape(P, L).astype(np.int64), rec[16:16 + P].astype(np.int32))
+        return rec
+
     def _sync_cache(self):
         if self._cache is None:
-            eng = self._eng()
-            obs = eng.observe(dtype=torch.int64)[0].cpu().numpy()
-            scores = eng.scores()[0].cpu().numpy().astype(np.int32)
-            self._cache = (obs, scores)
+            self._launch1()
         return self._cache
 
     # -- reference API -----------------------------------------------------------------------------
@@ -302,27 +341,30 @@ class SechsNimmtEnv:
         self._cache = None
         return self._create_states()
 
-    def step(self, action):
+    def step(self, action, rows=None):
         assert len(action) == self._num_players                     # env.py:67
-        eng = self._eng()
         cards = [int(c) for c in action]
-        acts = torch.tensor([[c if 0 <= c < 256 else 255 for c in cards]], dtype=torch.uint8).to(eng.device)
-        rewards, done = eng.step(acts)
-        packed = torch.cat([rewards.view(torch.uint8).flatten(), done, eng.illegal]).cpu().numpy()
         P = self._num_players
-        if packed[P + 1]:
+        if self._row_choice == "agent":
+            assert rows is not None and len(rows) == P, "row_choice='agent': step(action, rows) needs one row per player"
+            rows = [int(r) if 0 <= int(r) < 256 else 255 for r in rows]
+        else:
+            assert rows is None, "rows are only accepted with row_choice='agent'"
+        rec = self._launch1([c if 0 <= c < 256 else 255 for c in cards], rows)
+        if rec[P + 1]:
+            if rows is not None and any(not 0 <= r < NUM_ROWS for r in rows):
+                raise InvalidMoveException(f"Row choices {rows} must be in 0..{NUM_ROWS - 1}")
             # the device rejected the step and left the game untouched (env.py:68-69, 117-118)
             hands = self._hands
             for player, card in enumerate(cards):
                 if card not in hands[player]:
                     raise InvalidMoveException(f"Player {player + 1} tried to play card {card + 1}, but their hand is {hands[player]}")
             raise InvalidMoveException("illegal move")  # unreachable: device and host views agree
-        self._cache = None
         if self.verbose and logger.isEnabledFor(logging.DEBUG):
             for card, player in sorted((c, p) for p, c in enumerate(cards)):
                 logger.debug(f"{self._player_name(player)} plays card {card + 1}")
-        states = self._create_states()
-        return states, packed[:P].view(np.int8).astype(np.int32), bool(packed[P]), dict()
+        rewards, done = rec[:P].view(np.int8).astype(np.int32), bool(rec[P])
+        return self._create_states(), rewards, done, dict()
 
     def _create_states(self):
         obs, _ = self._sync_cache()

@@ -103,12 +103,27 @@ def policy_rollouts(roots, num_players, weights, n_mc, c_puct=2.0, root_rule=N.R
     return stats, probs
 
 
-def sharded_mcs_rollouts(roots, num_players, rollouts_per_action, seed=0, group=None, device=None):
-    """One decision batch spread over all ranks of the process group: stripe, play, all-reduce."""
+# Below this many rollouts in a decision batch, striping them over the ranks loses: the collective is pure latency (an
+# NCCL all-reduce of 240 bytes costs ~30 us on NVLink, measured in SCALE_r01: one root x 10 cards x 10,000 rollouts took
+# 36 us on one GPU and 58-66 us on 2-8), while the kernel is one wave of threads whatever the count (10^5 rollouts occupy a
+# third of one B200's resident threads).  Every rank then plays the WHOLE batch itself: same roots, same seed, same integers
+# on every rank — no communication at all, the latency of one GPU, and still the table the sharded path would produce.
+MIN_ROLLOUTS_TO_SHARD = 1_000_000
+
+
+def sharded_mcs_rollouts(roots, num_players, rollouts_per_action, seed=0, group=None, device=None, min_rollouts_to_shard=None):
+    """One decision batch on all ranks of the process group.  Large batches are striped over the ranks (rollout ids
+    ``id mod world``) and summed with the path's only collective; small ones (fewer than ``min_rollouts_to_shard``
+    rollouts in total, default MIN_ROLLOUTS_TO_SHARD) are played redundantly by every rank, which is faster than any
+    exchange and bit-identical (integer sums of the same rollout ids)."""
     import torch.distributed as dist
     rank, world = 0, 1
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
+    threshold = MIN_ROLLOUTS_TO_SHARD if min_rollouts_to_shard is None else int(min_rollouts_to_shard)
+    total = int(len(roots)) * MAX_ACTIONS * int(rollouts_per_action)
+    if world == 1 or total < threshold:
+        return mcs_rollouts(roots, num_players, rollouts_per_action, seed, 0, 1, device=device)
     stats = mcs_rollouts(roots, num_players, rollouts_per_action, seed, rank, world, device=device)
     return allreduce_stats(stats, group)
 

@@ -3,9 +3,15 @@ bookkeeping (``rl_6_nimmt/tournament.py``), for the evaluation harness of SURVEY
 
 ``scores`` are the session results: int [B, P] negative Hornochsen totals (``play.py:69-74``).  Everything is a handful
 of comparisons on the device; no host loop over games.  Pinned by ``tests/golden/position_stats.json`` (generated from the
-unmodified reference).  Elo (``multi_elo``, an unpinned third-party package absent from the reference tree) is not built.
+unmodified reference).  Elo (``Tournament._compute_elos``, tournament.py:157-164) runs on the device too (``elo_scan``); the
+``multi_elo`` package it calls is third-party and absent from the reference tree, so that one formula is stated, unit-tested
+against a plain restatement, and "parity unpinned".
 """
 import torch
+
+from . import _native as N
+
+ELO_INITIAL, ELO_K = 1600.0, 32.0     # Tournament.__init__ defaults (tournament.py:11)
 
 
 def absolute_positions(scores):
@@ -38,5 +44,30 @@ def summary(scores):
     over the batch: mean score, mean relative position and win rate per seat, as float64 tensors [P] on the device."""
     P = scores.shape[1]
     wins = torch.nn.functional.one_hot(winners(scores), P).to(torch.float64).mean(dim=0)
-    return {"mean_score": scores.to(torch.float64).mean(dim=0), "mean_relative_position": relative_positions(scores).to(torch.float64).mean(dim=0),
-            "win_rate": wins}
+    out = {"mean_score": scores.to(torch.float64).mean(dim=0), "mean_relative_position": relative_positions(scores).to(torch.float64).mean(dim=0),
+           "win_rate": wins}
+    if scores.is_cuda:
+        out["elo"] = elo_scan(scores)     # every seat from 1600, k = 32, the games in the order they were played
+    return out
+
+
+def elo_scan(scores, ratings=None, agents=None, k=ELO_K, want_history=False):
+    """``Tournament._compute_elos`` (tournament.py:157-164) applied to B finished games in order, on the device
+    (nimmt_elo_scan; formula in include/nimmt_b200.h).  scores: int [B,P] session results.  ratings: float64 [A] device tensor,
+    updated in place (default: ``ELO_INITIAL`` for P slots); agents: int32 [B,P] rating slot of every seat (default seat p =
+    slot p).  Returns ratings, or (ratings, history [B,P]) with ``want_history``."""
+    if not scores.is_cuda:
+        raise N.NimmtNativeError("elo_scan needs device tensors; there is no CPU fallback")
+    B, P = scores.shape
+    scores = scores.to(torch.int32).contiguous()
+    if ratings is None:
+        ratings = torch.full((P,), ELO_INITIAL, dtype=torch.float64, device=scores.device)
+    assert ratings.dtype == torch.float64 and ratings.is_cuda and ratings.is_contiguous()
+    if agents is not None:
+        agents = agents.to(device=scores.device, dtype=torch.int32).contiguous()
+        assert agents.shape == (B, P)
+    history = torch.empty((B, P), dtype=torch.float64, device=scores.device) if want_history else None
+    with torch.cuda.device(scores.device):
+        N.check(N.lib().nimmt_elo_scan(N.ptr(scores), N.ptr(agents), N.ptr(ratings), B, P, float(k), N.ptr(history),
+                                       torch.cuda.current_stream(scores.device).cuda_stream), "nimmt_elo_scan")
+    return (ratings, history) if want_history else ratings

@@ -35,15 +35,23 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def replay(P, rows0, hands0, actions):
+def replay(P, rows0, hands0, actions, row_choice=None):
+    """row_choice (int8 [n,T,P]): the free-row-choice mode, as oracle.replay."""
     rows0 = np.ascontiguousarray(rows0, np.int8)
     hands0 = np.ascontiguousarray(hands0, np.int8)
     actions = np.ascontiguousarray(actions, np.int8)
     n, T = actions.shape[:2]
     out = dict(rewards=np.zeros((n, T, P), np.int8), done=np.zeros((n, T), np.uint8), illegal=np.zeros((n, T), np.uint8),
                hands=np.zeros((n, T, P, 10), np.int8), boards=np.zeros((n, T, 4, 6), np.int8), scores=np.zeros((n, T, P), np.int16))
-    rc = lib().sim_replay(P, n, T, _p(rows0), _p(hands0), _p(actions), _p(out["rewards"]), _p(out["done"]), _p(out["illegal"]),
-                          _p(out["hands"]), _p(out["boards"]), _p(out["scores"]))
+    if row_choice is not None:
+        row_choice = np.ascontiguousarray(row_choice, np.int8)
+        assert row_choice.shape == actions.shape
+    lib().sim_set_row_choice(_p(row_choice) if row_choice is not None else None)
+    try:
+        rc = lib().sim_replay(P, n, T, _p(rows0), _p(hands0), _p(actions), _p(out["rewards"]), _p(out["done"]), _p(out["illegal"]),
+                              _p(out["hands"]), _p(out["boards"]), _p(out["scores"]))
+    finally:
+        lib().sim_set_row_choice(None)
     assert rc == 0
     return out
 

@@ -74,6 +74,8 @@ static void init_game(Game<P>& g, const int8_t* rows0 /*[4][6]*/, const int8_t* 
     }
 }
 
+static const int8_t* g_row_choice = nullptr;   // [n][turns][P] or NULL: the free-row-choice mode
+
 template <int P, class G>
 static void replay(int n, int turns, const int8_t* rows0, const int8_t* hands0, const int8_t* actions, int8_t* rewards,
                    uint8_t* done, uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores) {
@@ -82,9 +84,13 @@ static void replay(int n, int turns, const int8_t* rows0, const int8_t* hands0, 
         init_game<P>(g, rows0 + gi * 24, hands0 + gi * P * 10);
         for (int t = 0; t < turns; ++t) {
             const size_t gt = (size_t)gi * turns + t;
-            int act[P], pen[P];
+            int act[P], pen[P], choice[P];
             for (int p = 0; p < P; ++p) act[p] = (uint8_t)actions[gt * P + p];
-            const bool legal = step_game<P>(g, act, h_card_value, pen);
+            if (g_row_choice)
+                for (int p = 0; p < P; ++p) choice[p] = (uint8_t)g_row_choice[gt * P + p];
+            const bool legal = step_game<P>(g, act, h_card_value, pen, g_row_choice ? choice : nullptr);
+            if (!legal)
+                for (int p = 0; p < P; ++p) pen[p] = 0;
             illegal[gt] = !legal;
             done[gt] = game_done<P>(g);
             for (int p = 0; p < P; ++p) rewards[gt * P + p] = (int8_t)(-pen[p]);
@@ -120,12 +126,12 @@ static void tile_get(const uint8_t* tile, int lane, GameRec<P>& r) {
 }
 
 // kRandom: `actions` is OUTPUT (the cards the fused random step drew), keyed (seed, game0 + game, turn0 + t).
-template <int P, bool kRandom>
+template <int P, bool kRandom, bool kChoice = false>
 static void replay_tiles(int n, int turns, const int8_t* rows0, const int8_t* hands0, int8_t* actions, int8_t* rewards, uint8_t* done,
                          uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores, uint64_t seed, uint64_t game0) {
     using L = TileLayout<P>;
     alignas(16) static uint8_t tile[L::kTileBytes];
-    alignas(16) uint8_t acts[L::kActBytes];
+    alignas(16) uint8_t acts[L::kActBytes], chosen[L::kActBytes];
     uint8_t values5[128];
     for (int c = 0; c < 128; ++c) values5[c] = (uint8_t)(h_card_value[c] << 5);
     for (int first = 0; first < n; first += kTileGames) {
@@ -141,10 +147,12 @@ static void replay_tiles(int n, int turns, const int8_t* rows0, const int8_t* ha
                 const size_t gt = (size_t)(first + lane) * turns + t;
                 if (!kRandom)
                     for (int p = 0; p < P; ++p) acts[lane * P + p] = (uint8_t)actions[gt * P + p];
+                if (kChoice)
+                    for (int p = 0; p < P; ++p) chosen[lane * P + p] = (uint8_t)g_row_choice[gt * P + p];
                 alignas(16) uint32_t kw[4], ku[4];
                 uint8_t rew[P], dn = 0, ill = 0, drawn[P];
-                step_lane<P, kRandom>(tile, acts, lane, values5, kw, ku, rew, &dn, &ill, kRandom ? drawn : nullptr, seed, game0 + (uint64_t)(first + lane),
-                                      (uint32_t)t);
+                step_lane<P, kRandom, kChoice>(tile, acts, lane, values5, kw, ku, rew, &dn, &ill, kRandom ? drawn : nullptr, seed,
+                                               game0 + (uint64_t)(first + lane), (uint32_t)t, chosen);
                 for (int p = 0; p < P; ++p) {
                     rewards[gt * P + p] = (int8_t)rew[p];
                     if (kRandom) actions[gt * P + p] = (int8_t)drawn[p];
@@ -243,7 +251,11 @@ int sim_mcs(int P_, const nimmt_root* root, int64_t R, uint64_t seed, int rank, 
 int sim_replay(int P_, int n, int turns, const int8_t* rows0, const int8_t* hands0, const int8_t* actions, int8_t* rewards,
                uint8_t* done, uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores) {
     if (g_form == 2) {
-        DISPATCH(P_, (replay_tiles<P, false>(n, turns, rows0, hands0, const_cast<int8_t*>(actions), rewards, done, illegal, hands, boards, scores, 0, 0)));
+        if (g_row_choice) {
+            DISPATCH(P_, (replay_tiles<P, false, true>(n, turns, rows0, hands0, const_cast<int8_t*>(actions), rewards, done, illegal, hands, boards, scores, 0, 0)));
+        } else {
+            DISPATCH(P_, (replay_tiles<P, false>(n, turns, rows0, hands0, const_cast<int8_t*>(actions), rewards, done, illegal, hands, boards, scores, 0, 0)));
+        }
     } else if (g_form) { DISPATCH(P_, (replay<P, GameRec<P>>(n, turns, rows0, hands0, actions, rewards, done, illegal, hands, boards, scores))); }
     else { DISPATCH(P_, (replay<P, Game<P>>(n, turns, rows0, hands0, actions, rewards, done, illegal, hands, boards, scores))); }
     return 0;
@@ -266,6 +278,7 @@ int sim_random_actions(int P_, int n, const int8_t* rows0, const int8_t* hands0,
     return 0;
 }
 void sim_set_form(int form) { g_form = form; }
+void sim_set_row_choice(const int8_t* row_choice) { g_row_choice = row_choice; }
 // handrec.cuh directly: a hand of n ascending cards with `played` slots already empty; for every card id 0..255 the slot
 // rec_find reports (-1: not dealt), whether rec_take accepts it and the meta word it would commit; then the record's
 // views: rec_card per slot, rec_count, rec_to_mask words, rec_select for every k.

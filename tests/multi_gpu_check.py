@@ -29,6 +29,9 @@ def main():
     whole = R.mcs_rollouts(roots, 2, 100_003, seed=9)                    # every rank: the unsharded table
     assert torch.equal(sharded, whole), "sharded table differs from the unsharded one"
     assert sharded[0, :2, 2].tolist() == [100_003] * 2
+    # a small batch is played redundantly by every rank instead (no collective): same table as the unsharded call
+    small = R.sharded_mcs_rollouts(roots[:1], 2, 1000, seed=9)
+    assert torch.equal(small, R.mcs_rollouts(roots[:1], 2, 1000, seed=9)) and int(small[0, 0, 2]) == 1000
     # weak-scaling deal partition: rank r deals games [r*n, (r+1)*n) of the same seed
     n = 4096
     mine = BatchedSechsNimmtEnv(n, 4, seed=3, game0=rank * n).reset().observe(dtype=torch.int8)

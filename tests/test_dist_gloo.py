@@ -35,7 +35,19 @@ def _worker(rank, world, port, root_bytes, P, rollouts, seed, legal, out):
     before = stripe.clone()
     total = R.allreduce_stats(stripe)          # the product's collective wrapper
     action, means = R.choose_from_stats(legal, total[0].numpy())
-    out.put((rank, before.numpy(), total.numpy(), action, means))
+    # the product's front end (rollouts.sharded_mcs_rollouts) with the kernel launch replaced by the host build of the same
+    # rollout code: a small batch is played redundantly by every rank (no collective), a large one is striped + all-reduced
+    calls = []
+
+    def host_rollouts(roots, num_players, rollouts_per_action, seed=0, rank=0, world=1, out=None, device=None):
+        calls.append((rank, world))
+        return torch.from_numpy(mcs(num_players, bytes(roots[0]), rollouts_per_action, seed, rank=rank, world=world))[None]
+    R.mcs_rollouts = host_rollouts
+    roots = np.frombuffer(root_bytes, np.uint8)[None]
+    redundant = R.sharded_mcs_rollouts(roots, P, rollouts, seed)                              # 200,010 rollouts < MIN_ROLLOUTS_TO_SHARD
+    striped = R.sharded_mcs_rollouts(roots, P, rollouts, seed, min_rollouts_to_shard=1)
+    assert calls == [(0, 1), (rank, world)], calls
+    out.put((rank, before.numpy(), total.numpy(), action, means, redundant.numpy(), striped.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -60,8 +72,9 @@ def test_sharded_mcs_decision_world2():
     whole = mcs(m["P"], root, rollouts, seed)
     # stripes are disjoint and complete: counts add up, and the reduced table equals the single-rank table bit for bit
     assert res[0][1][0, :2, 2].tolist() == [10_001, 10_001] and res[1][1][0, :2, 2].tolist() == [10_000, 10_000]
-    for rank, _, total, action, means in res:
+    for rank, _, total, action, means, redundant, striped in res:
         assert (total[0] == whole).all()
+        assert (redundant[0] == whole).all() and (striped[0] == whole).all()
         assert action == 25                                   # E[25] = -2.68 > E[43] = -5.00 (KAT-C)
         assert abs(means[0] - m["exact"]["25"]["mean"]) < 0.1 and abs(means[1] - m["exact"]["43"]["mean"]) < 0.1
 

@@ -211,3 +211,122 @@ def test_full_size_replay_against_the_oracle_1m_games():
     assert not want["illegal"].any()
     for k, got in (("rewards", rewards), ("done", done), ("hands", hands), ("boards", boards), ("scores", scores)):
         assert np.array_equal(got, want[k]), k
+
+
+@pytest.mark.parametrize("P", [2, 4, 10])
+def test_free_row_choice_on_device(P):
+    """§8f row 4: the optional row_choice="agent" mode (the reference's TODO, env.py:156) — nimmt_step_choice through
+    k_step_tiles<P, false, true> (whole tiles) and k_step (ragged tail) against the oracle's list-based extension: random row
+    choices, every byte of every turn; invalid choices reject the step and leave the game untouched."""
+    n, T = 4096 + 19, 10
+    env = BatchedSechsNimmtEnv(n, P, seed=77 + P).reset()
+    obs0 = env.observe(dtype=torch.int8).cpu().numpy()
+    hands0, board0 = obs0[:, :, :10].copy(), obs0[:, 0, -24:].reshape(n, 4, 6).copy()
+    gen = torch.Generator(device="cuda").manual_seed(P)
+    # a rejected step first: every 50th game names row 4, every 77th row 255; those games stay as dealt, the others move on
+    a = env.random_actions().clone()
+    r = torch.randint(0, 4, (n, P), generator=gen, device="cuda", dtype=torch.uint8)
+    r[::50, 0] = 4
+    r[::77, P - 1] = 255
+    rew, dn = env.step(a, rows=r)
+    one = oracle.replay(P, board0, hands0, a.cpu().numpy().view(np.int8)[:, None], want_obs=False, row_choice=r.cpu().numpy().view(np.int8)[:, None])
+    bad = np.zeros(n, bool)
+    bad[::50] = True
+    bad[::77] = True
+    assert (env.illegal.cpu().numpy() == bad).all() and (one["illegal"][:, 0] == bad).all()
+    obs = env.observe(dtype=torch.int8).cpu().numpy()
+    assert np.array_equal(rew.cpu().numpy(), one["rewards"][:, 0]) and np.array_equal(obs[:, :, :10], one["hands"][:, 0])
+    assert np.array_equal(obs[:, 0, -24:].reshape(n, 4, 6), one["boards"][:, 0])
+    assert np.array_equal(obs[bad][:, :, :10], hands0[bad])                              # untouched
+    # then whole games with valid random choices
+    env.reset()
+    obs0 = env.observe(dtype=torch.int8).cpu().numpy()
+    hands0, board0 = obs0[:, :, :10].copy(), obs0[:, 0, -24:].reshape(n, 4, 6).copy()
+    acts, rows = np.zeros((n, T, P), np.int8), np.zeros((n, T, P), np.int8)
+    out = dict(rewards=np.zeros((n, T, P), np.int8), done=np.zeros((n, T), np.uint8), illegal=np.zeros((n, T), np.uint8),
+               hands=np.zeros((n, T, P, 10), np.int8), boards=np.zeros((n, T, 4, 6), np.int8), scores=np.zeros((n, T, P), np.int16))
+    for t in range(T):
+        a = env.random_actions().clone()
+        r = torch.randint(0, 4, (n, P), generator=gen, device="cuda", dtype=torch.uint8)
+        rew, dn = env.step(a, rows=r)
+        acts[:, t], rows[:, t] = a.cpu().numpy().view(np.int8), r.cpu().numpy().view(np.int8)
+        out["rewards"][:, t], out["done"][:, t], out["illegal"][:, t] = rew.cpu().numpy(), dn.cpu().numpy(), env.illegal.cpu().numpy()
+        obs = env.observe(dtype=torch.int8).cpu().numpy()
+        out["hands"][:, t], out["boards"][:, t], out["scores"][:, t] = obs[:, :, :10], obs[:, 0, -24:].reshape(n, 4, 6), env.scores().cpu().numpy()
+    want = oracle.replay(P, board0, hands0, acts, want_obs=False, row_choice=rows)
+    plain = oracle.replay(P, board0, hands0, acts, want_obs=False)
+    assert (want["rewards"] != plain["rewards"]).any() and not want["illegal"].any()
+    for k in ("rewards", "done", "illegal", "hands", "boards", "scores"):
+        assert np.array_equal(out[k], want[k]), k
+
+
+def test_free_row_choice_dropin():
+    """The B = 1 drop-in in agent mode (nimmt_step1 with rows): same game as the oracle, InvalidMoveException on a bad row."""
+    from rl_6_nimmt_b200.env import InvalidMoveException
+    np.random.seed(3)
+    env = SechsNimmtEnv(3, verbose=False, row_choice="agent")
+    states, legal = env.reset()
+    board0 = np.array([[r + [-1] * (6 - len(r)) for r in env._board]], np.int8)
+    hands0 = np.array([[h + [-1] * (10 - len(h)) for h in env._hands]], np.int8)
+    acts, rows, rewards = [], [], []
+    rng = np.random.RandomState(1)
+    with pytest.raises(InvalidMoveException):
+        env.step([l[0] for l in legal], rows=[0, 4, 0])
+    assert env._hands == [[int(c) for c in h if c >= 0] for h in hands0[0]]          # untouched
+    for t in range(10):
+        a = [l[rng.randint(len(l))] for l in legal]
+        r = rng.randint(0, 4, 3).tolist()
+        (states, legal), rew, done, _ = env.step(a, rows=r)
+        acts.append(a); rows.append(r); rewards.append(rew.tolist())
+    assert done
+    want = oracle.replay(3, board0, hands0, np.array([acts], np.int8), row_choice=np.array([rows], np.int8))
+    assert np.array_equal(np.array([rewards], np.int8), want["rewards"])
+    assert np.array_equal(np.stack(states).astype(np.int8), want["obs"][0, -1])
+    with pytest.raises(AssertionError):
+        SechsNimmtEnv(3, verbose=False).step([0, 1, 2], rows=[0, 0, 0])             # rows need row_choice="agent"
+
+
+def _elo_reference(scores, ratings, agents, k):
+    """Plain restatement of multi_elo.calc_elo as Tournament._compute_elos calls it (tournament.py:157-164): pairwise Elo,
+    K = k / (n - 1), S by place, all seats updated from the ratings before the game; games in order."""
+    ratings = ratings.copy()
+    hist = np.zeros(scores.shape, np.float64)
+    for b in range(len(scores)):
+        n = scores.shape[1]
+        old = [ratings[agents[b, p]] for p in range(n)]
+        for i in range(n):
+            d = 0.0
+            for j in range(n):
+                if i != j:
+                    s = 1.0 if scores[b, i] > scores[b, j] else (0.5 if scores[b, i] == scores[b, j] else 0.0)
+                    d += s - 1.0 / (1.0 + 10.0 ** ((old[j] - old[i]) / 400.0))
+            ratings[agents[b, i]] = old[i] + k / (n - 1) * d
+            hist[b, i] = ratings[agents[b, i]]
+    return ratings, hist
+
+
+def test_elo_scan_on_device():
+    """§8f row 4: Elo on the device (nimmt_elo_scan), sequential over the games like Tournament.score_game.  Known answers: two
+    equal players, k = 32 -> +-16; a draw between equals changes nothing; then random multi-player games with ties and a
+    seat -> agent map against the plain restatement above (1e-9), and the batched session's statistics."""
+    from rl_6_nimmt_b200 import stats as S
+    r = S.elo_scan(torch.tensor([[-3, -10]], device="cuda"))
+    assert np.allclose(r.cpu().numpy(), [1616.0, 1584.0])
+    r = S.elo_scan(torch.tensor([[-5, -5, -5]], device="cuda"))
+    assert np.allclose(r.cpu().numpy(), [1600.0] * 3)
+    rng = np.random.RandomState(0)
+    for P, A in ((2, 2), (4, 7), (10, 12)):
+        B = 300
+        scores = -rng.randint(0, 12, size=(B, P)).astype(np.int32)          # small range: plenty of ties
+        agents = np.stack([rng.choice(A, P, replace=False) for _ in range(B)]).astype(np.int32)
+        start = 1600.0 + 50.0 * rng.randn(A)
+        got, hist = S.elo_scan(torch.as_tensor(scores).cuda(), ratings=torch.as_tensor(start.copy()).cuda(), agents=torch.as_tensor(agents).cuda(),
+                               k=24.0, want_history=True)
+        want, want_hist = _elo_reference(scores, start, agents, 24.0)
+        assert np.abs(got.cpu().numpy() - want).max() < 1e-9 and np.abs(hist.cpu().numpy() - want_hist).max() < 1e-9
+        assert abs(got.sum().item() - start.sum()) < 1e-6                  # pairwise Elo is zero-sum
+    from rl_6_nimmt_b200.play import BatchedGameSession, MCSSeat, RandomSeat
+    sess = BatchedGameSession([MCSSeat(mc_max=50), RandomSeat(), RandomSeat()], 512, seed=2)
+    sess.play_games()
+    elo = sess.statistics()["elo"].cpu().numpy()
+    assert elo[0] > 1600 > max(elo[1], elo[2])                              # the searching seat gains rating against two DrunkHamsters

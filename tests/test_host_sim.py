@@ -107,6 +107,56 @@ def test_fused_random_step_in_tiles(P, form):
     assert (more["boards"][:, 0] == want["boards"][:, -1]).all()
 
 
+@pytest.mark.parametrize("P", [2, 4, 7, 10])
+def test_free_row_choice_vs_oracle(P, form):
+    """The optional row_choice="agent" mode (the reference's TODO, env.py:156): on an undercut the player takes the row they
+    named.  Stored-record form (step_game) and tile form (place_v3<kChoice>) against the oracle's list-based extension, with
+    random choices; choices outside 0..3 reject the step; and a directed case worked out by hand."""
+    if form == 0:
+        pytest.skip("the card-set form shares RowKeys::place with the stored-record form")
+    n = 2000
+    rng = np.random.RandomState(P)
+    hands, boards = deal(P, n, seed=200 + P)
+    acts = np.zeros((n, 10, P), np.int8)
+    rows = rng.randint(0, 4, size=(n, 10, P)).astype(np.int8)
+    rows[::97, 3, 0] = 4            # invalid choice: that step is rejected, the game continues with the same hands
+    rows[5::101, 6, P - 1] = -1
+    cur_h, cur_b = hands, boards
+    for t in range(10):
+        a = random_actions(P, cur_b, cur_h, seed=6, turn=t)
+        acts[:, t] = a.astype(np.int8)
+        step = oracle.replay(P, cur_b, cur_h, acts[:, t:t + 1], want_obs=False, row_choice=rows[:, t:t + 1])
+        cur_h, cur_b = step["hands"][:, 0], step["boards"][:, 0]
+    want = oracle.replay(P, boards, hands, acts, want_obs=False, row_choice=rows)
+    plain = oracle.replay(P, boards, hands, acts, want_obs=False)
+    assert want["illegal"][::97, 3].all() and want["illegal"].sum() == len(range(0, n, 97)) + len(range(5, n, 101))
+    assert (want["rewards"] != plain["rewards"]).any()          # the choices matter
+    got = replay(P, boards, hands, acts, row_choice=rows)
+    for k in ("rewards", "done", "illegal", "hands", "boards", "scores"):
+        assert (got[k] == want[k]).all(), k
+
+
+def test_free_row_choice_directed(form):
+    """Rows [10,1,1,1 bull heads]; player 0 undercuts with card 0 and names row 0: takes 10 (the default rule would take row 1)."""
+    if form == 0:
+        pytest.skip("see above")
+    board = -np.ones((1, 4, 6), np.int8)
+    board[0, 0, :2] = [54, 65]      # 7 + 5 ... card ids 54 -> 55 (7 heads), 65 -> 66 (5 heads): 12
+    board[0, 1, 0], board[0, 2, 0], board[0, 3, 0] = 20, 30, 40
+    hands = -np.ones((1, 2, 10), np.int8)
+    hands[0, 0, :2] = [0, 90]
+    hands[0, 1, :2] = [1, 91]
+    acts = np.array([[[0, 91]]], np.int8)
+    for choice, pen in ((0, 12), (1, 1), (3, 1)):
+        got = replay(2, board, hands, acts, row_choice=np.array([[[choice, 2]]], np.int8))
+        assert got["rewards"][0, 0].tolist() == [-pen, 0] and got["boards"][0, 0, choice].tolist() == [0, -1, -1, -1, -1, -1]
+        # 91 then lands on the row with the largest top below it: row 3 (40) once row 0 has been taken, else row 0 (65)
+        if choice == 0:
+            assert got["boards"][0, 0, 3].tolist()[:3] == [40, 91, -1]
+        else:
+            assert got["boards"][0, 0, 0].tolist()[:4] == [54, 65, 91, -1]
+
+
 def test_illegal_moves_untouched():
     P, n = 4, 500
     hands, boards = deal(P, n, seed=3)
