@@ -79,8 +79,13 @@ class MaskedPolicySeat:
 
 
 class BatchedGameSession:
-    def __init__(self, seats, num_games, device=None, seed=0):
+    """``data_parallel=True`` (under torch.distributed, one process per GPU): every rank plays its own ``num_games`` games and
+    all ranks train ONE net — the learning nets are broadcast from rank 0 at construction and their gradients are averaged
+    over the ranks at every step (train.allreduce_gradients), so the replicas never diverge.  Give every rank its own ``seed``."""
+
+    def __init__(self, seats, num_games, device=None, seed=0, data_parallel=False):
         self.seats = list(seats)
+        self.data_parallel = bool(data_parallel)
         self.env = BatchedSechsNimmtEnv(num_games, len(self.seats), device=device, seed=seed)
         self.lib, self.seed = N.lib(), int(seed)
         B, dev = num_games, self.env.device
@@ -102,8 +107,15 @@ class BatchedGameSession:
         for p, s in enumerate(self.seats):
             if isinstance(s, PolicySeat) and s.learn:
                 s.net.to(dev)
+                if id(s.net) not in self._learners and self.data_parallel:
+                    T.broadcast_parameters(s.net)
                 group = self._learners.setdefault(id(s.net), {"net": s.net, "seats": [], "optimizer": torch.optim.Adam(s.net.parameters())})
                 group["seats"].append(p)
+        if self.data_parallel:
+            for group in self._learners.values():
+                packed = PL.pack_weights(group["net"], device=dev)
+                for p in group["seats"]:
+                    self.seats[p].weights = packed
 
     def _stream(self):
         return torch.cuda.current_stream(self.env.device).cuda_stream
@@ -168,7 +180,8 @@ class BatchedGameSession:
         for group in self._learners.values():   # PolicyMCSAgent.learn at episode end, all episodes of all the net's seats at once
             obs = torch.cat([o for p in group["seats"] for o in seen_obs[p]])
             slot = torch.cat([c for p in group["seats"] for c in seen_slot[p]])
-            self.losses.append(T.imitation_step(group["net"], group["optimizer"], obs, slot, episodes=B * len(group["seats"])))
+            self.losses.append(T.imitation_step(group["net"], group["optimizer"], obs, slot, episodes=B * len(group["seats"]),
+                                                data_parallel=self.data_parallel))
             packed = PL.pack_weights(group["net"], device=env.device)
             for p in group["seats"]:
                 self.seats[p].weights = packed

@@ -36,11 +36,56 @@ def imitation_log_probs(net, obs, chosen_slot):
     return torch.where(legal.sum(dim=1) > 1, logp, torch.zeros_like(logp))
 
 
-def imitation_step(net, optimizer, obs, chosen_slot, episodes=1):
+def _world(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group)
+    return 1
+
+
+def broadcast_parameters(net, src=0, group=None):
+    """Data-parallel self-play starts from ONE net: rank ``src``'s parameters go to every rank (one flat buffer, one
+    broadcast).  No-op without a process group."""
+    import torch.distributed as dist
+    if _world(group) == 1:
+        return
+    params = [p.data for p in net.parameters()]
+    flat = torch.cat([p.reshape(-1) for p in params])
+    dist.broadcast(flat, src=src, group=group)
+    off = 0
+    for p in params:
+        p.copy_(flat[off:off + p.numel()].view_as(p))
+        off += p.numel()
+
+
+def allreduce_gradients(net, group=None):
+    """The data-parallel exchange of the self-play loop: the 15,101 gradient entries of the policy net
+    as ONE flat buffer, summed over the ranks (NCCL over NVLink: a 60 KB message, latency-bound) and divided by the world
+    size, so that every rank applies the gradient of the mean loss over ALL ranks' episodes and the replicas stay
+    identical.  No-op without a process group."""
+    import torch.distributed as dist
+    world = _world(group)
+    if world == 1:
+        return
+    grads = [p.grad for p in net.parameters() if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= world
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+def imitation_step(net, optimizer, obs, chosen_slot, episodes=1, data_parallel=False, group=None):
     """One Adam step on ``-sum log pi / episodes`` (``_train`` + ``_gradient_step``, agents/mcts.py:245-261).
-    Returns the loss as a 0-d tensor on the device (no host sync)."""
+    ``data_parallel``: every rank of the process group holds a replica of ``net`` and its own episodes; the gradients are
+    averaged over the ranks before the step (allreduce_gradients), i.e. all GPUs train ONE net on the mean loss of all
+    their episodes.  Returns this rank's loss as a 0-d tensor on the device (no host sync)."""
     loss = -imitation_log_probs(net, obs, chosen_slot).sum() / float(episodes)
     optimizer.zero_grad()
     loss.backward()
+    if data_parallel:
+        allreduce_gradients(net, group)
     optimizer.step()
     return loss.detach()

@@ -37,9 +37,21 @@ def main():
     mine = BatchedSechsNimmtEnv(n, 4, seed=3, game0=rank * n).reset().observe(dtype=torch.int8)
     full = BatchedSechsNimmtEnv(n * world, 4, seed=3).reset().observe(dtype=torch.int8)
     assert torch.equal(mine, full[rank * n:(rank + 1) * n])
+    # data-parallel Alpha0.5 self-play: every rank plays its own games, all ranks train ONE net (gradient all-reduce over NCCL)
+    from rl_6_nimmt_b200 import policy as PL
+    from rl_6_nimmt_b200.play import BatchedGameSession, PolicySeat
+    torch.manual_seed(1000 + rank)            # different initial nets: the session must broadcast rank 0's
+    net = PL.PolicyNet()
+    sess = BatchedGameSession([PolicySeat(net, mc_max=20, puct=True, learn=True) for _ in range(2)], 64, seed=50 + rank, data_parallel=True)
+    for _ in range(2):
+        sess.play_games()
+    flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    everyone = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(everyone, flat)
+    assert all(torch.equal(everyone[0], e) for e in everyone), "data-parallel replicas diverged"
     dist.barrier()
     if rank == 0:
-        print(f"multi_gpu_check ok on {world} GPUs: sharded MCS table bit-identical; split deals identical")
+        print(f"multi_gpu_check ok on {world} GPUs: sharded MCS table bit-identical; split deals identical; data-parallel self-play keeps one net")
     dist.destroy_process_group()
 
 

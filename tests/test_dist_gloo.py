@@ -94,3 +94,59 @@ def test_weak_scaling_game_partition():
         ranges.sort()
         assert ranges[0][0] == 0 and ranges[-1][1] == world * NSETS * B
         assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+
+
+def _dp_worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import rl_6_nimmt_b200  # noqa: F401
+    from rl_6_nimmt_b200 import policy as PL
+    from rl_6_nimmt_b200 import train as T
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    z = np.load(os.path.join(GOLDEN, "policy_train.npz"))
+    obs, chosen = torch.from_numpy(z["obs"]), torch.from_numpy(z["chosen"])
+    torch.manual_seed(100 + rank)               # the replicas START different: the broadcast must make them one net
+    net = PL.PolicyNet()
+    T.broadcast_parameters(net)
+    opt = torch.optim.Adam(net.parameters())
+    mine = slice(10 * rank, 10 * rank + 10)     # rank r trains on episode r
+    (-T.imitation_log_probs(net, obs[mine], chosen[mine]).sum()).backward()
+    T.allreduce_gradients(net)
+    grads = [p.grad.detach().numpy().copy() for p in net.parameters()]
+    for _ in range(2):
+        T.imitation_step(net, opt, obs[mine], chosen[mine], episodes=1, data_parallel=True)
+    out.put((rank, [p.detach().numpy().copy() for p in net.parameters()], grads))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_self_play_trains_one_net_world2():
+    """two ranks, each with its own episodes, train ONE net — parameters broadcast from rank 0,
+    the 15,101-entry gradient all-reduced (mean) before every Adam step.  The exchanged gradient is the gradient of the mean loss
+    over both ranks' episodes (checked against a single process), and after two steps the replicas are still bit-identical.
+    (Weights are not compared with the single process: where a gradient is rounding noise Adam's step is noise of size lr,
+    see test_train.py.)"""
+    import rl_6_nimmt_b200  # noqa: F401
+    from rl_6_nimmt_b200 import policy as PL
+    from rl_6_nimmt_b200 import train as T
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for a, b in zip(res[0][1], res[1][1]):
+        assert np.array_equal(a, b)                                   # the replicas never diverged
+    z = np.load(os.path.join(GOLDEN, "policy_train.npz"))
+    obs, chosen = torch.from_numpy(z["obs"]), torch.from_numpy(z["chosen"])
+    torch.manual_seed(100)                                            # rank 0's initial net
+    net = PL.PolicyNet()
+    (-T.imitation_log_probs(net, obs[:20], chosen[:20]).sum() / 2.0).backward()   # mean over the two episodes = mean of the ranks' losses
+    for g0, g1, p in zip(res[0][2], res[1][2], net.parameters()):
+        assert np.array_equal(g0, g1)
+        np.testing.assert_allclose(g0, p.grad.detach().numpy(), rtol=1e-4, atol=2e-6)
