@@ -121,6 +121,20 @@ NIMMT_API int nimmt_step(void *state, const uint8_t *actions, int8_t *rewards, u
 NIMMT_API int nimmt_observe(const void *state, void *obs, uint8_t *n_legal, int64_t num_games, int num_players,
                   int include_summaries, int dtype, void *stream);
 
+/* `turns` consecutive nimmt_step calls in ONE launch, for callers that hold the actions of several turns (replaying recorded
+ * games, scripted opponents): actions uint8 [T][B][P], rewards int8 [T][B][P], done / illegal uint8 [T][B] (illegal may be
+ * NULL) — exactly what T calls of nimmt_step on the slices would produce (an illegal turn leaves its game untouched and the
+ * next turn's cards are checked against the unchanged hands).  The packed state is read and written once per launch instead of
+ * once per step: a 32-game tile stays in shared memory for all T turns.  T <= 10; batches that are not a whole number of
+ * 32-game tiles are stepped with one launch per turn (B must then be a multiple of 16 for T > 1). */
+NIMMT_API int nimmt_step_many(void *state, const uint8_t *actions, int8_t *rewards, uint8_t *done, uint8_t *illegal,
+                              int64_t num_games, int num_players, int turns, void *stream);
+
+/* The same for random-vs-random play: `turns` consecutive nimmt_step_random calls (turn, turn + 1, ...) in one launch.
+ * actions (may be NULL) uint8 [T][B][P] receives the cards drawn; rewards int8 [T][B][P]; done uint8 [T][B]. */
+NIMMT_API int nimmt_step_random_many(void *state, uint8_t *actions, int8_t *rewards, uint8_t *done, int64_t num_games,
+                                     int num_players, uint64_t seed, uint32_t turn, uint64_t game0, int turns, void *stream);
+
 /* nimmt_step with the FREE ROW CHOICE of the real game, which the reference marks as a TODO (env.py:154-159, ":156 TODO: In the
  * long term this should be up to the agents"; README.md:11): rows uint8 [B][P] names, for every player, the row (0..3) they
  * take IF their card is lower than every row's top card; it replaces the lowest-penalty rule of _pick_row_to_replace and is

@@ -79,6 +79,36 @@ def run(P, B, what):
         moved = 12 * P + 24 + P + 4 * P + 24 + P + 2
         out.update(k_step_us=1e3 * ms, step_env_steps_per_s=B / (ms * 1e-3), step_moved_GBs=moved * B / (ms * 1e-3) / 1e9,
                    step_canonical_GBs=(36 * P + 49) * B / (ms * 1e-3) / 1e9)
+    if "many" in what:
+        # the same ten turns as ONE launch per batch (nimmt_step_many): the state stays in shared memory for all of them
+        stacked = [tp.clone() for tp in tapes]
+        rew = [torch.empty((10, B, P), dtype=torch.int8, device="cuda") for _ in range(nsets)]
+        dn = [torch.empty((10, B), dtype=torch.uint8, device="cuda") for _ in range(nsets)]
+        il = [torch.empty((10, B), dtype=torch.uint8, device="cuda") for _ in range(nsets)]
+
+        def many():
+            for e, tp, r, d, i in zip(envs, stacked, rew, dn, il):
+                e.step_many(tp, r, d, i)
+        redeal(); many(); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        redeal()
+        with torch.cuda.graph(g):
+            many()
+        ts = []
+        for _ in range(5):
+            redeal()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / (10 * nsets))
+        assert all(not bool(i.any()) and bool(d[9].all()) for i, d in zip(il, dn))
+        ms = statistics.median(ts)
+        out.update(step_many10_us_per_step=1e3 * ms, step_many10_env_steps_per_s=B / (ms * 1e-3))
+
+        def fused_many():
+            for e in envs:
+                e.reset(seed=e.seed)
+                e.step_random_many(10, rew[0], dn[0])
+        out["fused_many10_game_us_per_batch"] = 1e3 * graph_ms(fused_many, 1) / nsets      # deal + ten fused turns, one launch
     if "fused" in what:
         def fused():
             for e in envs:

@@ -95,15 +95,27 @@ struct StageLayout {
     static constexpr int kStride = (kBytes + 127) / 128 * 128;
 };
 
-template <int P, bool kRandom, bool kChoice = false>
+// kMany: `turns` consecutive env steps per launch (nimmt_step_many / nimmt_step_random_many).  A group's tiles stay in shared
+// memory for all of them: the state travels once per launch instead of once per step, the per-turn inputs (actions [T][B][P])
+// arrive with one more bulk copy per turn, and the per-turn outputs (rewards [T][B][P], done / illegal [T][B]) leave from
+// registers as before.  The stage size depends on `turns`, so the stage stride is a run-time value in this variant.
+template <int P, int W, bool kChoice>
+__host__ __device__ constexpr uint32_t stage_stride_many(int turns) {
+    return (uint32_t)((StageLayout<P, W, kChoice>::kActions + turns * W * TileLayout<P>::kActBytes + 127) / 128 * 128);
+}
+
+template <int P, bool kRandom, bool kChoice = false, bool kMany = false>
 __global__ void __launch_bounds__((StepShape<P>::kWarps + 1) * 32)
 k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restrict__ actions_out, int8_t* __restrict__ rewards,
              uint8_t* __restrict__ done, uint8_t* __restrict__ illegal, int num_tiles, uint64_t seed, uint32_t turn, uint64_t game0,
-             const uint8_t* __restrict__ rows = nullptr) {
+             const uint8_t* __restrict__ rows = nullptr, int turns = 1) {
     constexpr int W = StepShape<P>::kWarps, S = StepShape<P>::kStages;
     using L = TileLayout<P>;
     using G = StageLayout<P, W, kChoice>;
-    extern __shared__ __align__(128) uint8_t stage_smem[];   // S x G::kStride
+    static_assert(!(kMany && kChoice), "the multi-turn launch carries no row choices");
+    const uint32_t kStride = kMany ? stage_stride_many<P, W, kChoice>(kRandom ? 0 : turns) : (uint32_t)G::kStride;   // compile-time unless kMany
+    const int64_t turn_bytes = (int64_t)num_tiles * L::kActBytes;   // kMany: B * P, the stride between the turns of the [T][B][P] arrays
+    extern __shared__ __align__(128) uint8_t stage_smem[];   // S x kStride
     __shared__ uint64_t full[S], computed[S];
     __shared__ uint8_t values5[128];
     __shared__ uint4 keys_w[W * 32], keys_u[W * 32];          // each lane's row keys, indexable
@@ -127,10 +139,15 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
         auto load_group = [&](int group, int stage) {
             const int first = group * W;
             const uint32_t n = (uint32_t)min(W, num_tiles - first);       // the last group may be short
-            const uint32_t buf = stage_a + (uint32_t)stage * G::kStride, bar = full_a + 8u * (uint32_t)stage;
-            mbar_arrive_expect_tx_a(bar, n * (uint32_t)(L::kTileBytes + (kRandom ? 0 : L::kActBytes) + (kChoice ? L::kActBytes : 0)));
+            const uint32_t buf = stage_a + (uint32_t)stage * kStride, bar = full_a + 8u * (uint32_t)stage;
+            const uint32_t action_loads = kRandom ? 0u : (kMany ? (uint32_t)turns : 1u);
+            mbar_arrive_expect_tx_a(bar, n * ((uint32_t)L::kTileBytes + action_loads * (uint32_t)L::kActBytes + (kChoice ? (uint32_t)L::kActBytes : 0u)));
             bulk_load_a(buf, s.tile_ptr(first), n * L::kTileBytes, bar);
-            if constexpr (!kRandom) bulk_load_a(buf + G::kActions, actions + (int64_t)first * L::kActBytes, n * L::kActBytes, bar);
+            if constexpr (!kRandom) {
+                for (uint32_t t = 0; t < action_loads; ++t)
+                    bulk_load_a(buf + G::kActions + t * (uint32_t)(W * L::kActBytes), actions + (int64_t)t * turn_bytes + (int64_t)first * L::kActBytes,
+                                n * L::kActBytes, bar);
+            }
             if constexpr (kChoice) bulk_load_a(buf + G::kChoices, rows + (int64_t)first * L::kActBytes, n * L::kActBytes, bar);
         };
         const bool issuer = elect_one() != 0u;
@@ -146,7 +163,7 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
             if (issuer) {
                 const int first = group * W;
                 const int n = min(W, num_tiles - first);
-                const uint32_t buf = stage_a + (uint32_t)stage * G::kStride + L::kMeta;
+                const uint32_t buf = stage_a + (uint32_t)stage * kStride + L::kMeta;
                 for (int t = 0; t < n; ++t) bulk_store_a(s.mut_ptr(first + t), buf + (uint32_t)t * L::kTileBytes, L::kMutBytes);
                 bulk_commit();
                 const int next = group + S * (int)gridDim.x;
@@ -169,15 +186,25 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
     int stage = 0;
     uint32_t phase = 0;
     for (int group = blockIdx.x; group < num_groups; group += gridDim.x) {
-        uint8_t* tile = my_tile + stage * G::kStride;
+        uint8_t* tile = my_tile + stage * kStride;
         mbar_wait_a(full_a + 8u * (uint32_t)stage, phase);
         if (group * W + warp < num_tiles) {
             const int64_t g0 = (int64_t)group * (W * kTileGames);           // warp-uniform: lives on the uniform datapath
-            step_lane<P, kRandom, kChoice>(tile, stage_smem + stage * G::kStride + G::kActions + warp * L::kActBytes, lane, values5, kw, ku,
-                                           reinterpret_cast<uint8_t*>(rewards) + g0 * P + lane_game * P, done + g0 + lane_game,
-                                           illegal ? illegal + g0 + lane_game : nullptr, actions_out ? actions_out + g0 * P + lane_game * P : nullptr,
-                                           seed, game0 + (uint64_t)g0 + lane_game, turn,
-                                           stage_smem + stage * G::kStride + G::kChoices + warp * L::kActBytes);
+            uint8_t* stage_base = stage_smem + stage * kStride;
+            if constexpr (!kMany) {
+                step_lane<P, kRandom, kChoice>(tile, stage_base + G::kActions + warp * L::kActBytes, lane, values5, kw, ku,
+                                               reinterpret_cast<uint8_t*>(rewards) + g0 * P + lane_game * P, done + g0 + lane_game,
+                                               illegal ? illegal + g0 + lane_game : nullptr, actions_out ? actions_out + g0 * P + lane_game * P : nullptr,
+                                               seed, game0 + (uint64_t)g0 + lane_game, turn, stage_base + G::kChoices + warp * L::kActBytes);
+            } else {
+                const int64_t games = (int64_t)num_tiles * kTileGames;     // B: the stride between the turns of the per-game outputs
+                for (int t = 0; t < turns; ++t)                             // the tile never leaves shared memory between the turns
+                    step_lane<P, kRandom, false>(tile, stage_base + G::kActions + (t * W + warp) * L::kActBytes, lane, values5, kw, ku,
+                                                 reinterpret_cast<uint8_t*>(rewards) + (t * games + g0 + lane_game) * P, done + t * games + g0 + lane_game,
+                                                 illegal ? illegal + t * games + g0 + lane_game : nullptr,
+                                                 actions_out ? actions_out + (t * games + g0 + lane_game) * P : nullptr, seed,
+                                                 game0 + (uint64_t)g0 + lane_game, turn + (uint32_t)t);
+            }
             fence_async_smem();   // make this lane's shared-memory writes visible to the TMA engine
         }
         __syncwarp();
@@ -207,6 +234,26 @@ static int launch_step(const StateView& s, uint8_t* actions, int8_t* rewards, ui
     const int64_t tail0 = num_tiles * kTileGames;
     if (tail0 < s.B)   // ragged tail (< 32 games): plain loads
         k_step<P, kRandom><<<1, kStepThreads, 0, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, seed, turn, game0, tail0, rows);
+    return 0;
+}
+
+// `turns` consecutive steps in one launch.  Needs whole tiles (B % 32 == 0: the turns of the [T][B][P] arrays then start on
+// 16-byte boundaries); otherwise, and for a single turn, the caller falls back to one launch per turn.
+template <int P, bool kRandom>
+static int launch_step_many(const StateView& s, uint8_t* actions, int8_t* rewards, uint8_t* done, uint8_t* illegal, uint64_t seed, uint32_t turn,
+                            uint64_t game0, int turns, cudaStream_t st) {
+    constexpr int W = StepShape<P>::kWarps, S = StepShape<P>::kStages;
+    constexpr int kThreads = (W + 1) * 32;
+    const int64_t num_tiles = s.B / kTileGames;
+    const int smem = S * (int)stage_stride_many<P, W, false>(kRandom ? 0 : turns);
+    cudaFuncSetAttribute(k_step_tiles<P, kRandom, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // depends on `turns`: set per launch
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_tiles<P, kRandom, false, true>, kThreads, smem);
+    if (occ < 1) return NIMMT_E_UNSUPPORTED;
+    const int64_t groups = (num_tiles + W - 1) / W;
+    const unsigned blocks = (unsigned)min(groups, (int64_t)device_sms(current_device()) * occ);
+    k_step_tiles<P, kRandom, false, true><<<blocks, kThreads, smem, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, (int)num_tiles, seed,
+                                                                         turn, game0, nullptr, turns);
     return 0;
 }
 
@@ -249,6 +296,46 @@ int nimmt_step(void* state, const uint8_t* actions, int8_t* rewards, uint8_t* do
     StateView s(state, B, num_players);
     NIMMT_DISPATCH_P(num_players, (launch_step<P, false>(s, const_cast<uint8_t*>(actions), rewards, done, illegal, 0, 0, 0, (cudaStream_t)stream)));
     return check_launch();
+}
+
+int nimmt_step_many(void* state, const uint8_t* actions, int8_t* rewards, uint8_t* done, uint8_t* illegal, int64_t B, int num_players, int turns,
+                    void* stream) {
+    if (int rc = check_common(state, B, num_players)) return rc;
+    if (!actions || !rewards || !done || turns < 0 || turns > 10) return NIMMT_E_BADARG;
+    if (!aligned16(actions) || !aligned16(rewards) || !aligned16(done) || (illegal && !aligned16(illegal))) return NIMMT_E_ALIGN;
+    if (B == 0 || turns == 0) return NIMMT_OK;
+    if (turns == 1 || B % kTileGames != 0) {   // one launch per turn (ragged batches: the turns of [T][B][P] are not 16-byte aligned)
+        if (B % 16 != 0 && turns > 1) return NIMMT_E_ALIGN;
+        for (int t = 0; t < turns; ++t)
+            if (int rc = nimmt_step(state, actions + (int64_t)t * B * num_players, rewards + (int64_t)t * B * num_players, done + (int64_t)t * B,
+                                    illegal ? illegal + (int64_t)t * B : nullptr, B, num_players, stream))
+                return rc;
+        return NIMMT_OK;
+    }
+    StateView s(state, B, num_players);
+    int rc = 0;
+    NIMMT_DISPATCH_P(num_players, (rc = launch_step_many<P, false>(s, const_cast<uint8_t*>(actions), rewards, done, illegal, 0, 0, 0, turns, (cudaStream_t)stream)));
+    return rc ? rc : check_launch();
+}
+
+int nimmt_step_random_many(void* state, uint8_t* actions, int8_t* rewards, uint8_t* done, int64_t B, int num_players, uint64_t seed, uint32_t turn,
+                           uint64_t game0, int turns, void* stream) {
+    if (int rc = check_common(state, B, num_players)) return rc;
+    if (!rewards || !done || turns < 0 || turns > 10) return NIMMT_E_BADARG;
+    if ((actions && !aligned16(actions)) || !aligned16(rewards) || !aligned16(done)) return NIMMT_E_ALIGN;
+    if (B == 0 || turns == 0) return NIMMT_OK;
+    if (turns == 1 || B % kTileGames != 0) {
+        if (B % 16 != 0 && turns > 1) return NIMMT_E_ALIGN;
+        for (int t = 0; t < turns; ++t)
+            if (int rc = nimmt_step_random(state, actions ? actions + (int64_t)t * B * num_players : nullptr, rewards + (int64_t)t * B * num_players,
+                                           done + (int64_t)t * B, B, num_players, seed, turn + (uint32_t)t, game0, stream))
+                return rc;
+        return NIMMT_OK;
+    }
+    StateView s(state, B, num_players);
+    int rc = 0;
+    NIMMT_DISPATCH_P(num_players, (rc = launch_step_many<P, true>(s, actions, rewards, done, nullptr, seed, turn, game0, turns, (cudaStream_t)stream)));
+    return rc ? rc : check_launch();
 }
 
 int nimmt_step_choice(void* state, const uint8_t* actions, const uint8_t* rows, int8_t* rewards, uint8_t* done, uint8_t* illegal, int64_t B,

@@ -15,6 +15,16 @@
 // test-only: libnimmt_b200.so exports no host implementation of any entry point.
 #define NIMMT_HD __host__ __device__ __forceinline__
 
+// -DNIMMT_BOUNDS_CHECK: every data-dependent shared-memory index of the hot kernels is asserted in range (a device assert
+// traps the launch).  compute-sanitizer is closed on this pool's B200s, so this build — run over the small cases of
+// profiles/tools/sanitize_small.py and the GPU test suite — is the memory-safety evidence (profiles/README.md).
+#ifdef NIMMT_BOUNDS_CHECK
+#include <cassert>
+#define NIMMT_CHECK(cond) assert(cond)
+#else
+#define NIMMT_CHECK(cond) ((void)0)
+#endif
+
 namespace nimmt {
 
 NIMMT_HD int popc32(uint32_t x) {
@@ -369,6 +379,7 @@ NIMMT_HD uint32_t place_v3(uint32_t* w, uint32_t* u, uint32_t key, const uint8_t
     const bool take = under || len4 == 20u;                 // env.py:133: replaced, or the sixth card
     keep4 = take ? 0u : len4;
     const uint32_t base = take ? 0u : sumf;
+    NIMMT_CHECK((key >> 10) < (uint32_t)kCards && r < (uint32_t)kRows && keep4 <= 16u && (!kChoice || choice < (uint32_t)kRows));
     const uint32_t new_u = base + values5[key >> 10] + r;
     w[r * STRIDE] = (key & ~1023u) + new_u + keep4 + 4u;
     u[r * STRIDE] = new_u;

@@ -18,10 +18,11 @@ template <int P>
 __global__ void __launch_bounds__(kMcsThreads)
 k_mcs_rollouts(const nimmt_root* __restrict__ roots, int64_t local_rollouts, int iters, uint64_t seed, int rank, int world,
                unsigned long long* __restrict__ stats) {
-    __shared__ uint8_t values[128];
+    __shared__ uint8_t values[128], values5[128];
     __shared__ nimmt_root root;
     __shared__ long long red[3][kMcsThreads / 32];
     stage_card_values(values);
+    stage_card_values5(values5);
     const int d = blockIdx.z, a = blockIdx.y;
     if (threadIdx.x < 16) reinterpret_cast<uint32_t*>(&root)[threadIdx.x] = reinterpret_cast<const uint32_t*>(roots + d)[threadIdx.x];
     __syncthreads();
@@ -29,7 +30,7 @@ k_mcs_rollouts(const nimmt_root* __restrict__ roots, int64_t local_rollouts, int
     __shared__ RolloutRoot rr;
     __shared__ int root_ok;
     __shared__ __align__(4) uint8_t decks[kMcsThreads * kRolloutDeckStride];
-    __shared__ int keys_w[kRows * kMcsThreads], keys_u[kRows * kMcsThreads];   // row r of thread t at [r * threads + t]: conflict-free
+    __shared__ uint32_t keys_w[kRows * kMcsThreads], keys_u[kRows * kMcsThreads];   // row r of thread t at [r * threads + t]: conflict-free
     // cooperative version of make_rollout_root (rollout.cuh): thread c places card c at its rank in the
     // ascending pool / own lists, so building the 116-byte record costs ~20 instructions per thread
     {
@@ -70,7 +71,7 @@ k_mcs_rollouts(const nimmt_root* __restrict__ roots, int64_t local_rollouts, int
         if (i < local_rollouts) {
             const uint64_t j = (uint64_t)rank + (uint64_t)i * (uint64_t)world;
             const uint64_t id = ((uint64_t)d << 44) | ((uint64_t)a << 40) | j;
-            const int out = rollout<P, kMcsThreads>(rr, a, values, deck, keys_w + threadIdx.x, keys_u + threadIdx.x, seed, id);
+            const int out = rollout<P, kMcsThreads>(rr, a, values5, deck, keys_w + threadIdx.x, keys_u + threadIdx.x, seed, id);
             s += out; ss += (long long)out * out; cnt += 1;
         }
     }

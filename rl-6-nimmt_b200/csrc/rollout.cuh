@@ -95,10 +95,11 @@ template <int P, int I>
 NIMMT_HD void draw_opponents(TurnWords<P>& words, uint8_t* deck, uint32_t& drawn, uint32_t n_pool, int (&keys)[P]) {
     if constexpr (I < P) {
         const uint32_t j = drawn + words.template draw<I>(n_pool - drawn);
+        NIMMT_CHECK(j < n_pool && n_pool <= (uint32_t)kOwnOffset);
         const uint32_t card = deck[j];
         deck[j] = deck[drawn];   // position `drawn` is never read again: half a swap suffices
         ++drawn;
-        keys[I] = (int)(card << 4) | I;
+        keys[I] = (int)(card << 10) | (I << 6);   // place_v3's key: card << 10, the player (non-zero here) below
         draw_opponents<P, I + 1>(words, deck, drawn, n_pool, keys);
     }
 }
@@ -109,19 +110,19 @@ NIMMT_HD void draw_opponents(TurnWords<P>& words, uint8_t* deck, uint32_t& drawn
 // P-1 cards per turn from the pool prefix, player 0's card by swap-remove from its own list — a few
 // shared-memory byte accesses per draw instead of a popcount search through a 104-bit mask.
 // Returns the outcome (sum of player 0's rewards, <= 0).  Depends on (seed, rollout_id) only.
-// keys_w / keys_u: the caller's private row keys (game.cuh::place_indexed), row r at word r * KEY_STRIDE.
+// keys_w / keys_u: the caller's private row keys (game.cuh::place_v3), row r at word r * KEY_STRIDE.  values5: bull heads << 5.
 template <int P, int KEY_STRIDE = 1>
-NIMMT_HD int rollout(const RolloutRoot& rr, int first_index, const uint8_t* values, uint8_t* deck, int* keys_w, int* keys_u, uint64_t seed,
+NIMMT_HD int rollout(const RolloutRoot& rr, int first_index, const uint8_t* values5, uint8_t* deck, uint32_t* keys_w, uint32_t* keys_u, uint64_t seed,
                      uint64_t rollout_id) {
 #pragma unroll
     for (int w = 0; w < kRolloutDeckStride / 4; ++w) reinterpret_cast<uint32_t*>(deck)[w] = reinterpret_cast<const uint32_t*>(rr.deck)[w];
     Philox rng(seed, rollout_id, /*stream=*/0x6d637300u, 0);
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) { keys_w[r * KEY_STRIDE] = rr.board.w[r]; keys_u[r * KEY_STRIDE] = rr.board.u[r]; }
+    for (int r = 0; r < kRows; ++r) { keys_w[r * KEY_STRIDE] = (uint32_t)rr.board.w[r]; keys_u[r * KEY_STRIDE] = key_u_from_w((uint32_t)rr.board.w[r]); }
     int n_own = rr.n_own;
     uint32_t drawn = 0;
     const uint32_t n_pool = (uint32_t)rr.n_pool;
-    int outcome = 0;
+    uint32_t taken5 = 0;   // player 0's bull heads so far, << 5
     TurnWords<P> words;
     int turn = 0;
     while (n_own > 0) {
@@ -131,24 +132,23 @@ NIMMT_HD int rollout(const RolloutRoot& rr, int first_index, const uint8_t* valu
         {
             const uint32_t pick = words.template draw<0>((uint32_t)n_own);
             const uint32_t idx = turn == 0 ? (uint32_t)first_index : pick;
+            NIMMT_CHECK(idx < (uint32_t)n_own && n_own <= kHand);
             const int card = deck[kOwnOffset + idx];
             --n_own;
             deck[kOwnOffset + idx] = deck[kOwnOffset + n_own];   // swap-remove
-            keys[0] = card << 4;
+            keys[0] = card << 10;
         }
         draw_opponents<P, 1>(words, deck, drawn, n_pool, keys);
         sort_keys<P>(keys);
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-            const int card = keys[i] >> 4;
-            int row;
-            uint32_t keep_len;
-            const int pen = place_indexed<KEY_STRIDE>(keys_w, keys_u, card, values[card], row, keep_len);
-            outcome -= (keys[i] & 15) == 0 ? pen : 0;   // mcts.py:150: player 0's rewards only
+            uint32_t row, keep4;
+            const uint32_t pen5 = place_v3<KEY_STRIDE>(keys_w, keys_u, (uint32_t)keys[i], values5, row, keep4);
+            taken5 += (keys[i] & 0x3C0) == 0 ? pen5 : 0u;   // mcts.py:150: player 0's rewards only
         }
         ++turn;
     }
-    return outcome;
+    return -(int)(taken5 >> 5);
 }
 
 }  // namespace nimmt

@@ -184,6 +184,7 @@ NIMMT_HD void deal_game(uint64_t seed, uint64_t game_id, uint8_t* deck, int deck
         } else {
             off = below(spare, (uint32_t)(kCards - i));
         }
+        NIMMT_CHECK((uint32_t)i + off < (uint32_t)kCards);
         uint8_t* at = deck + i * deck_stride + off * (uint32_t)deck_stride;   // entry j = i + off
         const uint32_t card = *at;
         *at = deck[i * deck_stride];   // position i is never read again, so only half of the swap is needed

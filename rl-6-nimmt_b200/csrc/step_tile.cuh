@@ -95,6 +95,7 @@ NIMMT_HD void step_lane(uint8_t* tile, const uint8_t* acts, int lane, const uint
 #pragma unroll
             for (int r = 0; r < kRows; ++r) {
                 const uint32_t m = byte_perm(metas, 0u, 0x4440u + (uint32_t)r);
+                NIMMT_CHECK((m & 7u) >= 1u && (m & 7u) <= 5u);   // 1 <= len <= 5 between placements (env.py:133,170)
                 const uint32_t top = rec[4u * (m & 7u) + (uint32_t)r - 4u];
                 w[r] = top * 1024u + (m * 4u + (uint32_t)r);
                 u[r] = key_u_from_w(w[r]);
@@ -118,6 +119,7 @@ NIMMT_HD void step_lane(uint8_t* tile, const uint8_t* acts, int lane, const uint
             uint32_t choice = 0;
             if constexpr (kChoice) choice = rows[lane * P + ((key >> 6) & 15u)];          // the row this card's player named
             const uint32_t pen5 = place_v3<1, kChoice>(keys_w, keys_u, key, values5, row, keep4, choice);   // env.py:126-134
+            NIMMT_CHECK(keep4 + row < 20u && ((key >> 6) & 15u) < (uint32_t)P);
             rec[keep4 + row] = (uint8_t)(key >> 10);                                      // the one byte of the record a placement changes
             // env.py:167-169: the player of this card takes pen bull heads — added to its score field where the word lives,
             // in shared memory (the player is data: a register array would need a select per player)

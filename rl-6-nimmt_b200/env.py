@@ -168,6 +168,37 @@ class BatchedSechsNimmtEnv:
             raise InvalidMoveException(f"game {bad}: a played card is not in its owner's hand")
         return self.rewards, self.done
 
+    def step_many(self, actions, rewards=None, done=None, illegal=None):
+        """``T`` consecutive steps in one launch (nimmt_step_many): actions uint8 [T,B,P] device tensor -> (rewards int8 [T,B,P],
+        done uint8 [T,B], illegal uint8 [T,B]), exactly what T calls of :meth:`step` on the slices produce.  For callers that
+        hold the actions of several turns (replaying recorded games): the packed state is read and written once per launch,
+        a 32-game tile stays in shared memory for all T turns."""
+        T, B, P = actions.shape
+        assert (B, P) == (self.num_games, self.num_players) and actions.dtype == torch.uint8 and actions.is_cuda and 1 <= T <= 10
+        actions = actions.contiguous()
+        dev = self.device
+        rewards = torch.empty((T, B, P), dtype=torch.int8, device=dev) if rewards is None else rewards
+        done = torch.empty((T, B), dtype=torch.uint8, device=dev) if done is None else done
+        illegal = torch.empty((T, B), dtype=torch.uint8, device=dev) if illegal is None else illegal
+        with torch.cuda.device(dev):
+            N.check(self.lib.nimmt_step_many(N.ptr(self.state), N.ptr(actions), N.ptr(rewards), N.ptr(done), N.ptr(illegal), B, P, T,
+                                             self._stream()), "nimmt_step_many")
+        self.turn += T
+        return rewards, done, illegal
+
+    def step_random_many(self, turns, rewards=None, done=None, record_actions=False):
+        """``turns`` consecutive :meth:`step_random` calls in one launch (nimmt_step_random_many): random-vs-random play with the
+        state resident in shared memory.  Returns (rewards int8 [T,B,P], done uint8 [T,B], actions uint8 [T,B,P] or None)."""
+        T, B, P, dev = int(turns), self.num_games, self.num_players, self.device
+        rewards = torch.empty((T, B, P), dtype=torch.int8, device=dev) if rewards is None else rewards
+        done = torch.empty((T, B), dtype=torch.uint8, device=dev) if done is None else done
+        acts = torch.empty((T, B, P), dtype=torch.uint8, device=dev) if record_actions else None
+        with torch.cuda.device(dev):
+            N.check(self.lib.nimmt_step_random_many(N.ptr(self.state), N.ptr(acts), N.ptr(rewards), N.ptr(done), B, P, self._deal_seed(),
+                                                    self.turn, self.game0, T, self._stream()), "nimmt_step_random_many")
+        self.turn += T
+        return rewards, done, acts
+
     def host_out_buffer(self):
         """A pinned uint8 buffer for the packed form of step_host, plus views of its two parts:
         (buffer, rewards int8 [B,P], done_bits int32 [ceil(B/32)])."""

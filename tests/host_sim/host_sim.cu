@@ -224,12 +224,14 @@ static int mcs(const nimmt_root& root, int64_t R, uint64_t seed, int rank, int w
     RolloutRoot rr;
     if (!make_rollout_root<P>(root, h_card_value, rr)) return -2;
     alignas(4) uint8_t deck[kRolloutDeckStride];
+    uint8_t values5[128];
+    for (int c = 0; c < 128; ++c) values5[c] = (uint8_t)(h_card_value[c] << 5);
     const int n = rr.n_own;
     for (int a = 0; a < n; ++a) {
         for (int64_t j = rank; j < R; j += world) {
             const uint64_t id = ((uint64_t)a << 40) | (uint64_t)j;  // root index d = 0
-            alignas(16) int kw[4], ku[4];
-            const int out = rollout<P>(rr, a, h_card_value, deck, kw, ku, seed, id);
+            alignas(16) uint32_t kw[4], ku[4];
+            const int out = rollout<P>(rr, a, values5, deck, kw, ku, seed, id);
             stats[a * 3 + 0] += out; stats[a * 3 + 1] += (int64_t)out * out; stats[a * 3 + 2] += 1;
         }
     }

@@ -330,3 +330,45 @@ def test_elo_scan_on_device():
     sess.play_games()
     elo = sess.statistics()["elo"].cpu().numpy()
     assert elo[0] > 1600 > max(elo[1], elo[2])                              # the searching seat gains rating against two DrunkHamsters
+
+
+@pytest.mark.parametrize("P,n", [(4, 2048), (2, 96), (10, 1024), (4, 48), (7, 33 * 32)])
+def test_multi_turn_launch_equals_single_steps(P, n):
+    """nimmt_step_many / nimmt_step_random_many (the tile stays in shared memory for T turns) against T single launches: every
+    output byte and the final state identical; T = 1, 3, 7 and the whole game; whole tiles and a ragged batch (n = 48: one
+    launch per turn); an illegal turn in the middle leaves its games untouched and the later turns see the unchanged hands."""
+    ref = BatchedSechsNimmtEnv(n, P, seed=9).reset()
+    tape = torch.empty((10, n, P), dtype=torch.uint8, device="cuda")
+    want_rew = torch.empty((10, n, P), dtype=torch.int8, device="cuda")
+    want_done = torch.empty((10, n), dtype=torch.uint8, device="cuda")
+    for t in range(10):
+        ref.random_actions(out=tape[t])
+        rew, dn = ref.step(tape[t])
+        want_rew[t], want_done[t] = rew, dn
+    want_obs = ref.observe(dtype=torch.int8)
+    for split in ((10,), (3, 7), (1, 2, 3, 4)):
+        env = BatchedSechsNimmtEnv(n, P, seed=9).reset()
+        t0 = 0
+        for T in split:
+            rew, dn, ill = env.step_many(tape[t0:t0 + T])
+            assert torch.equal(rew, want_rew[t0:t0 + T]) and torch.equal(dn, want_done[t0:t0 + T]) and not bool(ill.any())
+            t0 += T
+        assert torch.equal(env.observe(dtype=torch.int8), want_obs) and torch.equal(env.scores(), ref.scores())
+    # an illegal turn (turn 2 replayed twice: its cards are gone) is rejected per game and does not disturb what follows
+    env = BatchedSechsNimmtEnv(n, P, seed=9).reset()
+    seq = torch.stack([tape[0], tape[1], tape[2], tape[2], tape[3]])
+    rew, dn, ill = env.step_many(seq)
+    assert bool(ill[3].all()) and not bool(ill[[0, 1, 2, 4]].any()) and bool((rew[3] == 0).all())
+    assert torch.equal(rew[4], want_rew[3]) and torch.equal(rew[2], want_rew[2])
+    # fused random play: the same cards, rewards and final state as step_random called turn by turn
+    a = BatchedSechsNimmtEnv(n, P, seed=13, game0=777).reset()
+    b = BatchedSechsNimmtEnv(n, P, seed=13, game0=777).reset()
+    rew_b, done_b, acts_b = b.step_random_many(4, record_actions=True)
+    for t in range(4):
+        rew, dn = a.step_random(record_actions=True)
+        assert torch.equal(rew, rew_b[t]) and torch.equal(dn, done_b[t]) and torch.equal(a._actions, acts_b[t])
+    rew_b, done_b, _ = b.step_random_many(6)
+    for t in range(6):
+        rew, dn = a.step_random()
+        assert torch.equal(rew, rew_b[t]) and torch.equal(dn, done_b[t])
+    assert bool(done_b[5].all()) and torch.equal(a.observe(dtype=torch.int8), b.observe(dtype=torch.int8))
