@@ -247,6 +247,23 @@ NIMMT_API int nimmt_policy_pack_weights(const float *w1, const float *b1, const 
 NIMMT_API int nimmt_policy_probs(const int8_t *obs, int64_t num_decisions, const void *weights, float *probs,
                                  float *logits, void *stream);
 
+/* ---- state-only 47 -> 100 -> 100 -> 104 nets (the model-free agents' shape) on the same tensor-core tile ---- */
+
+/* Bytes of the packed blob of a masked-policy net. */
+NIMMT_API size_t nimmt_masked_weights_bytes(void);
+
+/* HOST function.  Packs MultiHeadedMLP(47, (100, 100), (104,)) (MaskedReinforceAgent.actor, agents/policy.py:30-38; torch Linear
+ * layout: w1 [100][47], w2 [100][100], w3 [104][100], b3 [104]) with SechsNimmtStateNormalization(action=False) folded into
+ * layer 1, as nimmt_policy_pack_weights does for the 48 -> 100 -> 100 -> 1 net. */
+NIMMT_API int nimmt_masked_pack_weights(const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                                        const float *b3, void *blob_host);
+
+/* MaskedReinforceAgent.forward up to the sampling (agents/policy.py:45-50) for D decisions: obs int8 [D][47] (4-byte aligned
+ * base), probs float [D][10] = softmax of the net's card logits over the cards in hand, by hand slot (0 for empty slots);
+ * logits float [D][10] may be NULL.  bf16 operands, fp32 accumulation. */
+NIMMT_API int nimmt_masked_probs(const int8_t *obs, int64_t num_decisions, const void *weights, float *probs, float *logits,
+                                 void *stream);
+
 /* root-move rules of nimmt_policy_rollouts */
 #define NIMMT_ROOT_PUCT 0        /* PUCTAgent._choose_action_mc (agents/mcts.py:276-293) */
 #define NIMMT_ROOT_POLICY 1      /* PolicyMCSAgent._choose_action_mc (agents/mcts.py:209-217): sampled from the policy */

@@ -58,6 +58,9 @@ SIGNATURES = {
     "nimmt_policy_weights_bytes": (ctypes.c_size_t, []),
     "nimmt_policy_pack_weights": (_int, [_vp, _vp, _vp, _vp, _vp, ctypes.c_float, _vp]),
     "nimmt_policy_probs": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "nimmt_masked_weights_bytes": (ctypes.c_size_t, []),
+    "nimmt_masked_pack_weights": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nimmt_masked_probs": (_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "nimmt_policy_rollouts": (_int, [_vp, _int, _int, _vp, _int, ctypes.c_float, _int, _u64, _vp, _vp, _vp]),
     "nimmt_puct_choose": (_int, [_vp, _vp, _vp, _vp, _vp, _int, ctypes.c_float, _vp, _vp, _vp]),
 }

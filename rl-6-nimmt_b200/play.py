@@ -71,11 +71,13 @@ class ReinforceSeat:
 
 class MaskedPolicySeat:
     """A state-only net with one output per card at the table (MaskedReinforceAgent.forward, agents/policy.py:45-60; a DQN's
-    Q-values with ``greedy=True``): normalise the observation, one forward pass of ``net`` for all games (PyTorch on the
-    device: plain library GEMMs), restrict to the cards in hand, softmax, sample or take the argmax."""
+    Q-values with ``greedy=True``): normalise the observation, one forward pass of ``net`` for all games, restrict to the cards
+    in hand, softmax, sample or take the argmax.  Nets of the reference's shape, MultiHeadedMLP(47, (100, 100), (104,)), run on
+    the tcgen05 tile (nimmt_masked_probs, csrc/masked_policy.cu); any other ``net`` is evaluated by PyTorch on the device."""
 
     def __init__(self, net, greedy=False):
         self.net, self.greedy = net, bool(greedy)
+        self.weights = PL.pack_masked_weights(net)
 
 
 class BatchedGameSession:
@@ -144,8 +146,11 @@ class BatchedGameSession:
                         obs8 = env.observe(dtype=torch.int8)
                     mine = obs8[:, p].contiguous()
                     if isinstance(seat, MaskedPolicySeat):
-                        with torch.no_grad():
-                            probs = PL.masked_card_probs(seat.net.to(env.device), mine)
+                        if seat.weights is not None:
+                            probs = PL.masked_probs(mine, seat.weights.to(env.device))
+                        else:
+                            with torch.no_grad():
+                                probs = PL.masked_card_probs(seat.net.to(env.device), mine)
                     else:
                         probs = PL.policy_probs(mine, seat.weights)                # [B,10] by hand slot, 0 for empty slots
                     slot = probs.argmax(dim=1, keepdim=True) if seat.greedy else torch.multinomial(probs, 1, generator=self._generator)

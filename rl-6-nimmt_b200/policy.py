@@ -66,6 +66,46 @@ def masked_card_probs(net, obs):
     return torch.softmax(picked, dim=1)
 
 
+def pack_masked_weights(net, device=None):
+    """Packs a ``MultiHeadedMLP(47, (100, 100), (104,))`` (MaskedReinforceAgent's actor; a DQN's Q-net has the same shape) into the
+    device blob of nimmt_masked_probs.  Returns None if ``net`` does not have that parameter tree (the caller then evaluates it
+    with PyTorch on the device)."""
+    sd = {k: v.detach().to("cpu", torch.float32).contiguous().numpy() for k, v in net.state_dict().items()}
+    keys = ("latent_net.0.weight", "latent_net.0.bias", "latent_net.2.weight", "latent_net.2.bias", "head_nets.0.0.weight", "head_nets.0.0.bias")
+    if any(k not in sd for k in keys):
+        return None
+    w1, b1, w2, b2, w3, b3 = (sd[k] for k in keys)
+    if w1.shape != (100, 47) or w2.shape != (100, 100) or w3.shape != (104, 100):
+        return None
+    lib = N.lib()
+    blob = np.zeros(lib.nimmt_masked_weights_bytes(), np.uint8)
+    ptr = lambda a: np.ascontiguousarray(a).ctypes.data
+    N.check(lib.nimmt_masked_pack_weights(ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), blob.ctypes.data), "nimmt_masked_pack_weights")
+    t = torch.from_numpy(blob)
+    if device is not None or torch.cuda.is_available():
+        t = t.to(device if device is not None else "cuda")
+    return t
+
+
+def masked_probs(obs, weights, want_logits=False):
+    """MaskedReinforceAgent.forward up to the sampling on the tensor cores (nimmt_masked_probs): obs int8 [D,47] (device) ->
+    probabilities float32 [D,10] over the hand slots (0 for empty slots)."""
+    if not torch.cuda.is_available():
+        raise N.NimmtNativeError("masked_probs needs a CUDA device; there is no CPU fallback")
+    lib = N.lib()
+    assert obs.dtype == torch.int8 and obs.is_cuda and obs.dim() == 2 and obs.shape[1] == 47
+    obs = obs.contiguous()
+    if obs.data_ptr() % 4:
+        obs = obs.clone()
+    D = obs.shape[0]
+    probs = torch.empty((D, 10), dtype=torch.float32, device=obs.device)
+    logits = torch.empty((D, 10), dtype=torch.float32, device=obs.device) if want_logits else None
+    with torch.cuda.device(obs.device):
+        N.check(lib.nimmt_masked_probs(N.ptr(obs), D, N.ptr(weights), N.ptr(probs), N.ptr(logits),
+                                       torch.cuda.current_stream(obs.device).cuda_stream), "nimmt_masked_probs")
+    return (probs, logits) if want_logits else probs
+
+
 def torch_policy(net, state, legal_actions):
     """PolicyMCSAgent._compute_policy (agents/mcts.py:219-228) with autograd: probabilities over the legal cards."""
     state = torch.as_tensor(state, dtype=torch.float32).reshape(-1)

@@ -182,6 +182,25 @@ def test_masked_policy_probabilities_on_device():
             assert np.allclose(probs.sum(axis=1), 1.0, atol=1e-5)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+    # the same net on the tcgen05 tile (nimmt_masked_probs: bf16 operands, fp32 accumulate): against the reference's fp32
+    # probabilities to 2e-3, on the golden states and on 5,000 states of real games (three tiles and a ragged one, every hand size)
+    blob = PL.pack_masked_weights(net)
+    assert blob is not None
+    obs8 = torch.from_numpy(z["states"]).cuda()
+    probs, logits = PL.masked_probs(obs8, blob, want_logits=True)
+    assert np.abs(probs.cpu().numpy() - z["probs"]).max() < 2e-3, np.abs(probs.cpu().numpy() - z["probs"]).max()
+    assert ((probs > 0).sum(dim=1).cpu().numpy() == z["n_legal"]).all()
+    env = BatchedSechsNimmtEnv(500, 4, seed=3).reset()
+    states = []
+    for t in range(10):
+        states.append(env.observe(dtype=torch.int8)[:, t % 4].clone())
+        env.step_random()
+    states = torch.cat(states)[:4999].contiguous()
+    with torch.no_grad():
+        want = PL.masked_card_probs(net, states)
+    got = PL.masked_probs(states, blob)
+    assert float((got - want).abs().max()) < 2e-3, float((got - want).abs().max())
+    assert bool(((got > 0) == (states[:, :10] >= 0)).all()) and torch.allclose(got.sum(dim=1), torch.ones(4999, device="cuda"), atol=1e-5)
 
 
 def test_full_size_replay_against_the_oracle_1m_games():
