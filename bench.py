@@ -378,6 +378,43 @@ def run_ours(args):
     e2e_ms = statistics.median(e2e_runs)
     e2e_value = world * B * K2 / (e2e_ms * 1e-3)
 
+    # ---- the same end-to-end loop in the packed transfer format (nimmt_step_packed): 4-bit hand slots in, one bit record per game
+    # out — 2 + 3 bytes per 4-player game across PCIe instead of 4 + 4.1 ----
+    ab, rb = envs[0].packed_sizes()
+    h_slots = [torch.empty((10, B, ab), dtype=torch.uint8).pin_memory() for _ in range(NSETS)]
+    h_packed = [torch.empty((B, rb), dtype=torch.uint8).pin_memory() for _ in range(NSETS)]
+    for s_, env in enumerate(envs):
+        env.reset(seed=99 + s_)
+        dealt = env.observe(dtype=torch.int8)[:, :, :10].clone()
+        for t in range(10):
+            h_slots[s_][t].copy_(BatchedSechsNimmtEnv.pack_slots(h_actions[s_][t].to(dev), dealt))
+        del dealt
+    torch.cuda.synchronize()
+
+    def e2e_packed_cycle():
+        for s_, env in enumerate(envs):
+            with torch.cuda.stream(streams[s_]):
+                env.reset(seed=99 + s_)
+                for t in range(10):
+                    env.step_host_packed(h_slots[s_][t], h_packed[s_])
+
+    e2e_packed_cycle()
+    barrier()
+    g3 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g3):
+        cap = torch.cuda.current_stream(dev)
+        for st in streams:
+            st.wait_stream(cap)
+        e2e_packed_cycle()
+        for st in streams:
+            cap.wait_stream(st)
+    g3.replay()
+    e2e_packed_runs = [event_ms(lambda: [g3.replay() for _ in range(K2 // CYCLE)]) for _ in range(5)]
+    for s_, env in enumerate(envs):
+        _, dn_, il_ = env.unpack_results(h_packed[s_])
+        assert bool(dn_.all()) and not bool(il_.any()), "packed e2e replay diverged"
+    e2e_packed_value = world * B * K2 / (statistics.median(e2e_packed_runs) * 1e-3)
+
     # ---- also: the action generator alone, the fused random-play kernel, the B = 1 drop-in ----
     def graph_ms(fn, launches_in_graph, reps=5):
         fn()
@@ -488,7 +525,7 @@ def run_ours(args):
     # ---- BASELINE configs[4]: ten-player max-table sweep, the games split evenly over the ranks (weak per-rank timing, max over ranks) ----
     sweep = []
     free_bytes = torch.cuda.mem_get_info(dev)[0]
-    del envs, tapes, h_actions, h_out, streams, g_cycle, g_rem, g_fin, g_deal, g_steps, g2, session
+    del envs, tapes, h_actions, h_out, h_slots, h_packed, streams, g_cycle, g_rem, g_fin, g_deal, g_steps, g2, g3, session
     torch.cuda.empty_cache()
     for lg in args.sweep_log2:
         total_games = 1 << lg
@@ -545,7 +582,10 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": bytes_per_step(P) * B, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * P, "d2h_bytes_per_step": (B * P + 15) // 16 * 16 + 4 * ((B + 31) // 32), "steps": K2,
                 "runs": [world * B * K2 / (m * 1e-3) for m in e2e_runs], "reported": "median of 5 runs of `steps` steps",
-                "api": "BatchedSechsNimmtEnv.step_host (pinned host actions in; rewards int8 [B,P] + done as one bit per game out in one copy), 4 batches on 4 streams, 40-step cycles replayed as a CUDA graph"},
+                "api": "BatchedSechsNimmtEnv.step_host (pinned host actions in; rewards int8 [B,P] + done as one bit per game out in one copy), 4 batches on 4 streams, 40-step cycles replayed as a CUDA graph",
+                "packed": {"value": e2e_packed_value, "unit": UNIT, "h2d_bytes_per_step": B * ab, "d2h_bytes_per_step": B * rb,
+                           "runs": [world * B * K2 / (m * 1e-3) for m in e2e_packed_runs],
+                           "api": "BatchedSechsNimmtEnv.step_host_packed: 4-bit hand slots in, one bit record per game (5 bits of bull heads per player, done, illegal) out; same loop, same graph structure"}},
         "gpu_launches": timed_launches,
         "clocks": clocks,
         "also": {"k_random_actions_ms": ra_ms, "k_deal_ms": kdeal_ms,

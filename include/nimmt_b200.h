@@ -135,6 +135,18 @@ NIMMT_API int nimmt_step_many(void *state, const uint8_t *actions, int8_t *rewar
 NIMMT_API int nimmt_step_random_many(void *state, uint8_t *actions, int8_t *rewards, uint8_t *done, int64_t num_games,
                                      int num_players, uint64_t seed, uint32_t turn, uint64_t game0, int turns, void *stream);
 
+/* nimmt_step in a compact TRANSFER format, for hosts that feed actions and read results over PCIe every step (the step itself is
+ * the same; about 5 bytes per 4-player game cross the bus instead of 8.1):
+ *   slots    uint8 [B][ceil(P/2)]  one 4-bit HAND SLOT per player instead of a card byte: player p = nibble (p & 1) of byte p >> 1;
+ *                                  slot s = the s-th card of the hand AS DEALT, ascending (what the first observation showed);
+ *                                  a slot >= 10, or one whose card has been played, rejects the step like an illegal card
+ *   results  uint8 [B][ceil((5P+2)/8)]  little-endian bit record per game: bits [5p, 5p+5) the bull heads player p took this
+ *                                  step (reward = minus that, env.py:169), bit 5P done, bit 5P+1 illegal
+ * nimmt_packed_bytes returns the two record sizes.  B must be a multiple of 32. */
+NIMMT_API int nimmt_packed_bytes(int num_players, int *action_bytes, int *result_bytes);
+NIMMT_API int nimmt_step_packed(void *state, const uint8_t *slots, uint8_t *results, int64_t num_games, int num_players,
+                                void *stream);
+
 /* nimmt_step with the FREE ROW CHOICE of the real game, which the reference marks as a TODO (env.py:154-159, ":156 TODO: In the
  * long term this should be up to the agents"; README.md:11): rows uint8 [B][P] names, for every player, the row (0..3) they
  * take IF their card is lower than every row's top card; it replaces the lowest-penalty rule of _pick_row_to_replace and is

@@ -45,6 +45,8 @@ SIGNATURES = {
     "nimmt_step1": (_int, [_vp, _i64, _vp, _vp, _int, _int, _vp, _vp]),
     "nimmt_step_many": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
     "nimmt_step_random_many": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _u64, _u32, _u64, _int, _vp]),
+    "nimmt_packed_bytes": (_int, [_int, _vp, _vp]),
+    "nimmt_step_packed": (_int, [_vp, _vp, _vp, _i64, _int, _vp]),
     "nimmt_step_choice": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp]),
     "nimmt_pack_flags": (_int, [_vp, _vp, _i64, _vp]),
     "nimmt_observe": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp]),

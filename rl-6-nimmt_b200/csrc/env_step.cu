@@ -85,14 +85,18 @@ struct StepShape {
     static constexpr int kStages = P <= 5 ? NIMMT_STEP_STAGES_SMALL : NIMMT_STEP_STAGES_LARGE;
 };
 
-template <int P, int W, bool kChoice = false>
+template <int P, int W, bool kChoice = false, bool kPacked = false>
 struct StageLayout {
     using L = TileLayout<P>;
     static constexpr int kTiles = 0;                                          // W tile records
-    static constexpr int kActions = W * L::kTileBytes;                        // W x 32 x P action bytes
-    static constexpr int kChoices = kActions + W * L::kActBytes;              // kChoice: W x 32 x P row-choice bytes
-    static constexpr int kBytes = kChoices + (kChoice ? W * L::kActBytes : 0);
+    static constexpr int kActions = W * L::kTileBytes;                        // W x 32 x P action bytes (kPacked: 4-bit slots)
+    static constexpr int kActTile = kPacked ? kTileGames * packed_action_bytes<P>() : L::kActBytes;   // action bytes of one tile
+    static constexpr int kChoices = kActions + W * kActTile;                  // kChoice: W x 32 x P row-choice bytes
+    static constexpr int kResults = kChoices;                                 // kPacked: W x 32 bit-packed result records (bulk-stored)
+    static constexpr int kResTile = kTileGames * packed_result_bytes<P>();
+    static constexpr int kBytes = kChoices + (kChoice ? W * L::kActBytes : 0) + (kPacked ? W * kResTile : 0);
     static constexpr int kStride = (kBytes + 127) / 128 * 128;
+    static_assert(kActTile % 16 == 0 && kResTile % 16 == 0, "bulk copies need 16-byte alignment");
 };
 
 // kMany: `turns` consecutive env steps per launch (nimmt_step_many / nimmt_step_random_many).  A group's tiles stay in shared
@@ -104,15 +108,18 @@ __host__ __device__ constexpr uint32_t stage_stride_many(int turns) {
     return (uint32_t)((StageLayout<P, W, kChoice>::kActions + turns * W * TileLayout<P>::kActBytes + 127) / 128 * 128);
 }
 
-template <int P, bool kRandom, bool kChoice = false, bool kMany = false>
+// kPacked: the compact transfer format (step_tile.cuh): `actions` holds 4-bit hand slots, and `rewards` receives ONE bit-packed
+// record per game (bull heads, done, illegal) — staged in shared memory by the lanes and bulk-stored by the producer.
+template <int P, bool kRandom, bool kChoice = false, bool kMany = false, bool kPacked = false>
 __global__ void __launch_bounds__((StepShape<P>::kWarps + 1) * 32)
 k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restrict__ actions_out, int8_t* __restrict__ rewards,
              uint8_t* __restrict__ done, uint8_t* __restrict__ illegal, int num_tiles, uint64_t seed, uint32_t turn, uint64_t game0,
              const uint8_t* __restrict__ rows = nullptr, int turns = 1) {
     constexpr int W = StepShape<P>::kWarps, S = StepShape<P>::kStages;
     using L = TileLayout<P>;
-    using G = StageLayout<P, W, kChoice>;
+    using G = StageLayout<P, W, kChoice, kPacked>;
     static_assert(!(kMany && kChoice), "the multi-turn launch carries no row choices");
+    static_assert(!kPacked || (!kRandom && !kChoice && !kMany), "the packed format exists for the plain step only");
     const uint32_t kStride = kMany ? stage_stride_many<P, W, kChoice>(kRandom ? 0 : turns) : (uint32_t)G::kStride;   // compile-time unless kMany
     const int64_t turn_bytes = (int64_t)num_tiles * L::kActBytes;   // kMany: B * P, the stride between the turns of the [T][B][P] arrays
     extern __shared__ __align__(128) uint8_t stage_smem[];   // S x kStride
@@ -141,12 +148,12 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
             const uint32_t n = (uint32_t)min(W, num_tiles - first);       // the last group may be short
             const uint32_t buf = stage_a + (uint32_t)stage * kStride, bar = full_a + 8u * (uint32_t)stage;
             const uint32_t action_loads = kRandom ? 0u : (kMany ? (uint32_t)turns : 1u);
-            mbar_arrive_expect_tx_a(bar, n * ((uint32_t)L::kTileBytes + action_loads * (uint32_t)L::kActBytes + (kChoice ? (uint32_t)L::kActBytes : 0u)));
+            mbar_arrive_expect_tx_a(bar, n * ((uint32_t)L::kTileBytes + action_loads * (uint32_t)G::kActTile + (kChoice ? (uint32_t)L::kActBytes : 0u)));
             bulk_load_a(buf, s.tile_ptr(first), n * L::kTileBytes, bar);
             if constexpr (!kRandom) {
                 for (uint32_t t = 0; t < action_loads; ++t)
-                    bulk_load_a(buf + G::kActions + t * (uint32_t)(W * L::kActBytes), actions + (int64_t)t * turn_bytes + (int64_t)first * L::kActBytes,
-                                n * L::kActBytes, bar);
+                    bulk_load_a(buf + G::kActions + t * (uint32_t)(W * G::kActTile), actions + (int64_t)t * turn_bytes + (int64_t)first * G::kActTile,
+                                n * G::kActTile, bar);
             }
             if constexpr (kChoice) bulk_load_a(buf + G::kChoices, rows + (int64_t)first * L::kActBytes, n * L::kActBytes, bar);
         };
@@ -165,6 +172,9 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
                 const int n = min(W, num_tiles - first);
                 const uint32_t buf = stage_a + (uint32_t)stage * kStride + L::kMeta;
                 for (int t = 0; t < n; ++t) bulk_store_a(s.mut_ptr(first + t), buf + (uint32_t)t * L::kTileBytes, L::kMutBytes);
+                if constexpr (kPacked)
+                    bulk_store_a(reinterpret_cast<uint8_t*>(rewards) + (int64_t)first * G::kResTile, stage_a + (uint32_t)stage * kStride + G::kResults,
+                                 (uint32_t)n * G::kResTile);
                 bulk_commit();
                 const int next = group + S * (int)gridDim.x;
                 if (next < num_groups) {
@@ -191,7 +201,10 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
         if (group * W + warp < num_tiles) {
             const int64_t g0 = (int64_t)group * (W * kTileGames);           // warp-uniform: lives on the uniform datapath
             uint8_t* stage_base = stage_smem + stage * kStride;
-            if constexpr (!kMany) {
+            if constexpr (kPacked) {
+                step_lane<P, false, false, true>(tile, stage_base + G::kActions + warp * G::kActTile, lane, values5, kw, ku,
+                                                 stage_base + G::kResults + (warp * kTileGames + lane) * packed_result_bytes<P>(), nullptr, nullptr, nullptr, 0, 0, 0);
+            } else if constexpr (!kMany) {
                 step_lane<P, kRandom, kChoice>(tile, stage_base + G::kActions + warp * L::kActBytes, lane, values5, kw, ku,
                                                reinterpret_cast<uint8_t*>(rewards) + g0 * P + lane_game * P, done + g0 + lane_game,
                                                illegal ? illegal + g0 + lane_game : nullptr, actions_out ? actions_out + g0 * P + lane_game * P : nullptr,
@@ -214,26 +227,28 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
 }
 
 // kRandom = false: actions is the tape to play; true: actions (may be NULL) receives the cards drawn in the kernel.
-template <int P, bool kRandom, bool kChoice = false>
+template <int P, bool kRandom, bool kChoice = false, bool kPacked = false>
 static int launch_step(const StateView& s, uint8_t* actions, int8_t* rewards, uint8_t* done, uint8_t* illegal, uint64_t seed, uint32_t turn,
                        uint64_t game0, cudaStream_t st, const uint8_t* rows = nullptr) {
     constexpr int W = StepShape<P>::kWarps, S = StepShape<P>::kStages;
-    constexpr int kSmem = S * StageLayout<P, W, kChoice>::kStride;
+    constexpr int kSmem = S * StageLayout<P, W, kChoice, kPacked>::kStride;
     constexpr int kThreads = (W + 1) * 32;
     const int64_t num_tiles = s.B / kTileGames;
     if (num_tiles > 0) {
         static int occ_cache[kMaxDevices];   // per device: the shared-memory opt-in and the occupancy are device properties
-        const int blocks_per_sm = blocks_per_sm_cached(k_step_tiles<P, kRandom, kChoice>, kThreads, kSmem, occ_cache);
+        const int blocks_per_sm = blocks_per_sm_cached(k_step_tiles<P, kRandom, kChoice, false, kPacked>, kThreads, kSmem, occ_cache);
         const int num_sms = device_sms(current_device());
         // persistent grid: one resident wave; block b walks groups b, b + #blocks, ...
         const int64_t groups = (num_tiles + W - 1) / W;
         const unsigned blocks = (unsigned)min(groups, (int64_t)num_sms * blocks_per_sm);
-        k_step_tiles<P, kRandom, kChoice><<<blocks, kThreads, kSmem, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, (int)num_tiles,
-                                                                          seed, turn, game0, rows);
+        k_step_tiles<P, kRandom, kChoice, false, kPacked><<<blocks, kThreads, kSmem, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal,
+                                                                                          (int)num_tiles, seed, turn, game0, rows);
     }
     const int64_t tail0 = num_tiles * kTileGames;
-    if (tail0 < s.B)   // ragged tail (< 32 games): plain loads
-        k_step<P, kRandom><<<1, kStepThreads, 0, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, seed, turn, game0, tail0, rows);
+    if (tail0 < s.B) {   // ragged tail (< 32 games): plain loads
+        if constexpr (kPacked) return NIMMT_E_UNSUPPORTED;   // checked by the entry point: the packed format needs whole tiles
+        else k_step<P, kRandom><<<1, kStepThreads, 0, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal, seed, turn, game0, tail0, rows);
+    }
     return 0;
 }
 
@@ -335,6 +350,26 @@ int nimmt_step_random_many(void* state, uint8_t* actions, int8_t* rewards, uint8
     StateView s(state, B, num_players);
     int rc = 0;
     NIMMT_DISPATCH_P(num_players, (rc = launch_step_many<P, true>(s, actions, rewards, done, nullptr, seed, turn, game0, turns, (cudaStream_t)stream)));
+    return rc ? rc : check_launch();
+}
+
+int nimmt_packed_bytes(int num_players, int* action_bytes, int* result_bytes) {
+    if (num_players < 1 || num_players > kMaxPlayers) return NIMMT_E_BADARG;
+    if (action_bytes) *action_bytes = (num_players + 1) / 2;
+    if (result_bytes) *result_bytes = (5 * num_players + 2 + 7) / 8;
+    return NIMMT_OK;
+}
+
+int nimmt_step_packed(void* state, const uint8_t* slots, uint8_t* results, int64_t B, int num_players, void* stream) {
+    if (int rc = check_common(state, B, num_players)) return rc;
+    if (!slots || !results) return NIMMT_E_BADARG;
+    if (!aligned16(slots) || !aligned16(results)) return NIMMT_E_ALIGN;
+    if (B % kTileGames != 0) return NIMMT_E_UNSUPPORTED;   // whole 32-game tiles only (pad the batch)
+    if (B == 0) return NIMMT_OK;
+    StateView s(state, B, num_players);
+    int rc = 0;
+    NIMMT_DISPATCH_P(num_players, (rc = launch_step<P, false, false, true>(s, const_cast<uint8_t*>(slots), reinterpret_cast<int8_t*>(results), nullptr, nullptr, 0,
+                                                                           0, 0, (cudaStream_t)stream)));
     return rc ? rc : check_launch();
 }
 

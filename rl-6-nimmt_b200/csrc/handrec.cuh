@@ -59,6 +59,12 @@ NIMMT_HD uint32_t rec_card(const HandRec& h, int slot) {
     return slot < 8 ? low : high;
 }
 
+// The same for a slot known only at run time, by byte permutes instead of variable shifts (slot < 10).
+NIMMT_HD uint32_t rec_card_dyn(const HandRec& h, uint32_t slot) {
+    const uint32_t low = byte_perm(h.lo.x, h.lo.y, slot & 7u), high = byte_perm(h.meta, 0u, slot & 1u);
+    return (slot < 8u ? low : high) & 0x7Fu;   // stored bytes are < 0x80 (0x7F = none); bit 7 of the meta bytes is an empty flag
+}
+
 // The slot that was dealt `card`, as that slot's EMPTY BIT of the meta word (0 if the hand never held the card).  Exact for
 // card < 128 (ids 104..126 match nothing; 127 matches only never-dealt slots, whose empty bits are set from the start);
 // larger ids may return garbage and must be rejected by the caller.  Branch-free and mostly multiplies, which run on the FMA

@@ -24,7 +24,16 @@ struct TileLayout {
 // Returns the game's rewards packed one byte per player (P <= 4: one word; larger P: stored through `rew_out`).
 //   kChoice  free-row-choice mode: `rows` holds, like `acts`, one byte per (game, player) — the row that player takes if their
 //            card undercuts every row (0..3; anything else rejects the step like an illegal card)
-template <int P, bool kRandom, bool kChoice = false>
+//   kPacked  the compact transfer format for hosts on the far side of PCIe (nimmt_step_packed): `acts` holds one 4-bit HAND SLOT
+//            per player (player p = nibble p & 1 of byte p >> 1 of the game's ceil(P / 2) bytes; slot s = the s-th card of the
+//            hand AS DEALT, ascending) instead of card bytes, and the results leave as one bit-packed record per game through
+//            `rew_out`: bits [5 p, 5 p + 5) the bull heads player p took, bit 5 P done, bit 5 P + 1 illegal
+template <int P>
+constexpr int packed_action_bytes() { return (P + 1) / 2; }
+template <int P>
+constexpr int packed_result_bytes() { return (5 * P + 2 + 7) / 8; }
+
+template <int P, bool kRandom, bool kChoice = false, bool kPacked = false>
 NIMMT_HD void step_lane(uint8_t* tile, const uint8_t* acts, int lane, const uint8_t* values5, uint32_t* keys_w, uint32_t* keys_u,
                                           uint8_t* rew_out, uint8_t* done_out, uint8_t* illegal_out, uint8_t* act_out, uint64_t seed,
                                           uint64_t game_id, uint32_t turn, const uint8_t* rows = nullptr) {
@@ -58,6 +67,19 @@ NIMMT_HD void step_lane(uint8_t* tile, const uint8_t* acts, int lane, const uint
 #pragma unroll
             for (int p = 0; p < P; ++p) a[p] = (int)act[p];
             store_bytes<P>(act_out, 0, a);
+        }
+    } else if constexpr (kPacked) {
+        // the slot is given: the card is read, not searched; legal iff the slot exists and still holds its card
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const uint32_t slot = ((uint32_t)acts[lane * packed_action_bytes<P>() + (p >> 1)] >> (4 * (p & 1))) & 15u;
+            HandRec h;
+            h.lo = cards0[p * kTileGames];
+            h.meta = meta0[p * kTileGames];
+            const uint32_t bit = slot < (uint32_t)kHand ? rec_slot_mask(slot) & ~h.meta : 0u;
+            act[p] = rec_card_dyn(h, slot < (uint32_t)kHand ? slot : 0u);
+            meta[p] = h.meta | bit;
+            legal = legal && bit != 0u;
         }
     } else {
         // env.py:68-69 — every card is checked before anything is touched
@@ -132,6 +154,16 @@ NIMMT_HD void step_lane(uint8_t* tile, const uint8_t* acts, int lane, const uint
         const uint4 fw = *reinterpret_cast<const uint4*>(keys_w);
         *reinterpret_cast<uint32_t*>(rec + 20) = byte_perm(byte_perm(fw.x >> 2, fw.y >> 2, 0x0040u), byte_perm(fw.z >> 2, fw.w >> 2, 0x0040u), 0x5410u);
         done = (meta[0] & kEmptyBits) == kEmptyBits;   // env.py:246-249
+    }
+    if constexpr (kPacked) {
+        // one bit-packed record per game: 5 bits of bull heads per player (<= 27), then done and illegal
+        uint64_t rec64 = 0;
+#pragma unroll
+        for (int p = 0; p < P; ++p) rec64 |= (uint64_t)((0u - (gain[p] >> kRecScoreShift)) & 31u) << (5 * p);   // gain's top byte is -(bull heads)
+        rec64 |= (uint64_t)(done ? 1u : 0u) << (5 * P) | (uint64_t)(legal ? 0u : 1u) << (5 * P + 1);
+#pragma unroll
+        for (int b = 0; b < packed_result_bytes<P>(); ++b) rew_out[b] = (uint8_t)(rec64 >> (8 * b));
+        return;
     }
     // rewards (env.py:169): byte p = top byte of gain[p]; gathered with byte permutes, stored with the widest access P allows
     if constexpr (P % 4 == 0) {

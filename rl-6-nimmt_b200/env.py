@@ -199,6 +199,58 @@ class BatchedSechsNimmtEnv:
         self.turn += T
         return rewards, done, acts
 
+    # -- the compact transfer format (nimmt_step_packed): for hosts that feed actions and read results over PCIe every step --
+    def packed_sizes(self):
+        """(action bytes, result bytes) per game of the packed format: ceil(P/2) and ceil((5P+2)/8)."""
+        P = self.num_players
+        return (P + 1) // 2, (5 * P + 2 + 7) // 8
+
+    @staticmethod
+    def pack_slots(cards, dealt_hands):
+        """cards [B,P] (any integer dtype) + the hands AS DEALT [B,P,10] (the first observation's hand blocks, ascending) ->
+        uint8 [B, ceil(P/2)]: one 4-bit hand slot per player (15 where the card is not in the dealt hand: an illegal move)."""
+        hit = dealt_hands.to(torch.int16) == cards.to(torch.int16).unsqueeze(2)
+        slot = torch.where(hit.any(dim=2), hit.to(torch.uint8).argmax(dim=2), torch.full_like(cards, 15, dtype=torch.int64)).to(torch.uint8)
+        if slot.shape[1] % 2:
+            slot = torch.cat([slot, torch.zeros_like(slot[:, :1])], dim=1)
+        return (slot[:, 0::2] | (slot[:, 1::2] << 4)).contiguous()
+
+    def unpack_results(self, packed):
+        """uint8 [B, ceil((5P+2)/8)] -> (rewards int8 [B,P], done bool [B], illegal bool [B])."""
+        P = self.num_players
+        rec = torch.zeros(packed.shape[0], dtype=torch.int64, device=packed.device)
+        for b in range(packed.shape[1]):
+            rec |= packed[:, b].to(torch.int64) << (8 * b)
+        rewards = torch.stack([-((rec >> (5 * p)) & 31) for p in range(P)], dim=1).to(torch.int8)
+        return rewards, ((rec >> (5 * P)) & 1).bool(), ((rec >> (5 * P + 1)) & 1).bool()
+
+    def step_packed(self, slots, out=None):
+        """:meth:`step` in the packed transfer format: slots uint8 [B, ceil(P/2)] device tensor (:meth:`pack_slots`) ->
+        uint8 [B, ceil((5P+2)/8)] bit records (:meth:`unpack_results`).  B must be a multiple of 32."""
+        ab, rb = self.packed_sizes()
+        assert slots.shape == (self.num_games, ab) and slots.dtype == torch.uint8 and slots.is_cuda
+        slots = slots.contiguous()
+        if out is None:
+            out = torch.empty((self.num_games, rb), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.nimmt_step_packed(N.ptr(self.state), N.ptr(slots), N.ptr(out), self.num_games, self.num_players, self._stream()),
+                    "nimmt_step_packed")
+        self.turn += 1
+        return out
+
+    def step_host_packed(self, slots_host, results_host):
+        """step_host in the packed format: H2D copy of ``slots_host`` (pinned uint8 [B, ceil(P/2)]), the step, ONE D2H copy of the
+        bit records into ``results_host`` (pinned uint8 [B, ceil((5P+2)/8)]).  5 bytes per 4-player game cross PCIe instead of
+        8.1.  Nothing synchronises."""
+        if not hasattr(self, "_slots_dev"):
+            ab, rb = self.packed_sizes()
+            self._slots_dev = torch.empty((self.num_games, ab), dtype=torch.uint8, device=self.device)
+            self._packed_dev = torch.empty((self.num_games, rb), dtype=torch.uint8, device=self.device)
+        self._slots_dev.copy_(slots_host, non_blocking=True)
+        self.step_packed(self._slots_dev, self._packed_dev)
+        results_host.copy_(self._packed_dev, non_blocking=True)
+        return results_host
+
     def host_out_buffer(self):
         """A pinned uint8 buffer for the packed form of step_host, plus views of its two parts:
         (buffer, rewards int8 [B,P], done_bits int32 [ceil(B/32)])."""

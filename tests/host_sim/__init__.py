@@ -27,7 +27,9 @@ def lib():
 
 def set_form(form):
     """0: the per-game logic on 104-bit card sets (Game<P>); 1: on the stored hand records (GameRec<P>, handrec.cuh);
-    2: in place in 32-game tile records through step_tile.cuh::step_lane, the per-lane code of k_step_tiles."""
+    2: in place in 32-game tile records through step_tile.cuh::step_lane, the per-lane code of k_step_tiles;
+    3: the same with the compact transfer format (4-bit hand slots in, bit-packed results out; the slots are relative to hands0,
+    so hands0 must be the hands as dealt, or whatever reset_to was given)."""
     lib().sim_set_form(int(form))
 
 

@@ -126,7 +126,7 @@ static void tile_get(const uint8_t* tile, int lane, GameRec<P>& r) {
 }
 
 // kRandom: `actions` is OUTPUT (the cards the fused random step drew), keyed (seed, game0 + game, turn0 + t).
-template <int P, bool kRandom, bool kChoice = false>
+template <int P, bool kRandom, bool kChoice = false, bool kPacked = false>
 static void replay_tiles(int n, int turns, const int8_t* rows0, const int8_t* hands0, int8_t* actions, int8_t* rewards, uint8_t* done,
                          uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores, uint64_t seed, uint64_t game0) {
     using L = TileLayout<P>;
@@ -145,14 +145,30 @@ static void replay_tiles(int n, int turns, const int8_t* rows0, const int8_t* ha
         for (int t = 0; t < turns; ++t) {
             for (int lane = 0; lane < lanes; ++lane) {
                 const size_t gt = (size_t)(first + lane) * turns + t;
-                if (!kRandom)
+                if (!kRandom && !kPacked)
                     for (int p = 0; p < P; ++p) acts[lane * P + p] = (uint8_t)actions[gt * P + p];
+                if (kPacked) {   // the transfer format: the card's slot in the hand as dealt (hands0, ascending), 15 if it was never there
+                    for (int b = 0; b < packed_action_bytes<P>(); ++b) acts[lane * packed_action_bytes<P>() + b] = 0;
+                    for (int p = 0; p < P; ++p) {
+                        int slot = 15;
+                        for (int i = 0; i < 10; ++i)
+                            if (hands0[((size_t)(first + lane) * P + p) * 10 + i] == actions[gt * P + p] && actions[gt * P + p] >= 0) slot = i;
+                        acts[lane * packed_action_bytes<P>() + (p >> 1)] |= (uint8_t)(slot << (4 * (p & 1)));
+                    }
+                }
                 if (kChoice)
                     for (int p = 0; p < P; ++p) chosen[lane * P + p] = (uint8_t)g_row_choice[gt * P + p];
                 alignas(16) uint32_t kw[4], ku[4];
-                uint8_t rew[P], dn = 0, ill = 0, drawn[P];
-                step_lane<P, kRandom, kChoice>(tile, acts, lane, values5, kw, ku, rew, &dn, &ill, kRandom ? drawn : nullptr, seed,
-                                               game0 + (uint64_t)(first + lane), (uint32_t)t, chosen);
+                uint8_t rew[P + 8], dn = 0, ill = 0, drawn[P];
+                step_lane<P, kRandom, kChoice, kPacked>(tile, acts, lane, values5, kw, ku, rew, &dn, &ill, kRandom ? drawn : nullptr, seed,
+                                                        game0 + (uint64_t)(first + lane), (uint32_t)t, chosen);
+                if (kPacked) {   // unpack the bit record: 5 bits of bull heads per player, done, illegal
+                    uint64_t rec = 0;
+                    for (int b = 0; b < packed_result_bytes<P>(); ++b) rec |= (uint64_t)rew[b] << (8 * b);
+                    for (int p = 0; p < P; ++p) rew[p] = (uint8_t)(0 - (int)((rec >> (5 * p)) & 31u));
+                    dn = (uint8_t)((rec >> (5 * P)) & 1u);
+                    ill = (uint8_t)((rec >> (5 * P + 1)) & 1u);
+                }
                 for (int p = 0; p < P; ++p) {
                     rewards[gt * P + p] = (int8_t)rew[p];
                     if (kRandom) actions[gt * P + p] = (int8_t)drawn[p];
@@ -252,7 +268,9 @@ int sim_mcs(int P_, const nimmt_root* root, int64_t R, uint64_t seed, int rank, 
 }
 int sim_replay(int P_, int n, int turns, const int8_t* rows0, const int8_t* hands0, const int8_t* actions, int8_t* rewards,
                uint8_t* done, uint8_t* illegal, int8_t* hands, int8_t* boards, int16_t* scores) {
-    if (g_form == 2) {
+    if (g_form == 3) {
+        DISPATCH(P_, (replay_tiles<P, false, false, true>(n, turns, rows0, hands0, const_cast<int8_t*>(actions), rewards, done, illegal, hands, boards, scores, 0, 0)));
+    } else if (g_form == 2) {
         if (g_row_choice) {
             DISPATCH(P_, (replay_tiles<P, false, true>(n, turns, rows0, hands0, const_cast<int8_t*>(actions), rewards, done, illegal, hands, boards, scores, 0, 0)));
         } else {

@@ -391,3 +391,49 @@ def test_multi_turn_launch_equals_single_steps(P, n):
         rew, dn = a.step_random()
         assert torch.equal(rew, rew_b[t]) and torch.equal(dn, done_b[t])
     assert bool(done_b[5].all()) and torch.equal(a.observe(dtype=torch.int8), b.observe(dtype=torch.int8))
+
+
+@pytest.mark.parametrize("P,n", [(4, 4096), (2, 64), (10, 1024), (5, 96)])
+def test_packed_transfer_format_equals_the_byte_format(P, n):
+    """nimmt_step_packed (4-bit hand slots in, one bit record per game out — the PCIe-frugal form of the end-to-end path) against
+    nimmt_step on the same games: rewards, done, illegal and the state after every turn; a replayed turn (cards already played)
+    and out-of-range slots are rejected per game."""
+    a = BatchedSechsNimmtEnv(n, P, seed=21).reset()
+    b = BatchedSechsNimmtEnv(n, P, seed=21).reset()
+    dealt = a.observe(dtype=torch.int8)[:, :, :10].clone()
+    assert a.packed_sizes() == ((P + 1) // 2, (5 * P + 2 + 7) // 8)
+    for t in range(10):
+        cards = a.random_actions().clone()
+        rew, dn = a.step(cards)
+        packed = BatchedSechsNimmtEnv.pack_slots(cards, dealt)
+        if t == 4:
+            # slot 15 for player 0 of every third game: those games are rejected and untouched, the others step; the second call
+            # with the right slots steps exactly the rejected ones (the others' cards are gone: rejected in turn)
+            bad = packed.clone()
+            bad[::3, 0] |= 0x0F
+            r1, d1, i1 = b.unpack_results(b.step_packed(bad))
+            b.turn -= 1
+            want_bad = torch.zeros(n, dtype=torch.bool, device="cuda")
+            want_bad[::3] = True
+            assert torch.equal(i1, want_bad) and bool((r1[want_bad] == 0).all())
+            r2, d2, i2 = b.unpack_results(b.step_packed(packed))
+            assert torch.equal(i2, ~want_bad) and bool((r2[~want_bad] == 0).all())
+            rew_p, done_p = torch.where(want_bad.unsqueeze(1), r2, r1), torch.where(want_bad, d2, d1)
+        else:
+            rew_p, done_p, ill_p = b.unpack_results(b.step_packed(packed))
+            assert not bool(ill_p.any())
+        assert torch.equal(rew_p, rew) and torch.equal(done_p, dn.bool())
+        assert torch.equal(a.observe(dtype=torch.int8), b.observe(dtype=torch.int8)) and torch.equal(a.scores(), b.scores())
+    assert bool(done_p.all())
+    # host buffers: one H2D + one D2H per step
+    c = BatchedSechsNimmtEnv(n, P, seed=21).reset()
+    ab, rb = c.packed_sizes()
+    h_in, h_out = torch.empty((n, ab), dtype=torch.uint8).pin_memory(), torch.empty((n, rb), dtype=torch.uint8).pin_memory()
+    ref = BatchedSechsNimmtEnv(n, P, seed=21).reset()
+    cards = ref.random_actions().clone()
+    rew, dn = ref.step(cards)
+    h_in.copy_(BatchedSechsNimmtEnv.pack_slots(cards, dealt).cpu())
+    c.step_host_packed(h_in, h_out)
+    torch.cuda.synchronize()
+    rew_p, done_p, ill_p = c.unpack_results(h_out)
+    assert torch.equal(rew_p, rew.cpu()) and not bool(ill_p.any())

@@ -11,11 +11,12 @@ from conftest import GOLDEN
 from host_sim import deal, lib, play_random_tiles, random_actions, replay, set_form
 
 
-@pytest.fixture(autouse=True, params=[0, 1, 2], ids=["card-sets", "stored-records", "tile-records"])
+@pytest.fixture(autouse=True, params=[0, 1, 2, 3], ids=["card-sets", "stored-records", "tile-records", "tile-records-packed-io"])
 def form(request):
     """Every test runs on all forms of the per-game logic: 104-bit card sets (Game<P>), the stored hand records
     (GameRec<P>, handrec.cuh), and 32-game tile records stepped in place by step_tile.cuh::step_lane — the exact per-lane
-    code of the throughput kernel k_step_tiles (placement by game.cuh::place_v3)."""
+    code of the throughput kernel k_step_tiles (placement by game.cuh::place_v3) — also with the compact transfer format of
+    nimmt_step_packed (4-bit hand slots in, one bit record per game out)."""
     set_form(request.param)
     yield request.param
     set_form(0)
@@ -112,8 +113,8 @@ def test_free_row_choice_vs_oracle(P, form):
     """The optional row_choice="agent" mode (the reference's TODO, env.py:156): on an undercut the player takes the row they
     named.  Stored-record form (step_game) and tile form (place_v3<kChoice>) against the oracle's list-based extension, with
     random choices; choices outside 0..3 reject the step; and a directed case worked out by hand."""
-    if form == 0:
-        pytest.skip("the card-set form shares RowKeys::place with the stored-record form")
+    if form in (0, 3):
+        pytest.skip("the card-set form shares RowKeys::place with the stored-record form; the packed format carries no row choices")
     n = 2000
     rng = np.random.RandomState(P)
     hands, boards = deal(P, n, seed=200 + P)
@@ -138,7 +139,7 @@ def test_free_row_choice_vs_oracle(P, form):
 
 def test_free_row_choice_directed(form):
     """Rows [10,1,1,1 bull heads]; player 0 undercuts with card 0 and names row 0: takes 10 (the default rule would take row 1)."""
-    if form == 0:
+    if form in (0, 3):
         pytest.skip("see above")
     board = -np.ones((1, 4, 6), np.int8)
     board[0, 0, :2] = [54, 65]      # 7 + 5 ... card ids 54 -> 55 (7 heads), 65 -> 66 (5 heads): 12
