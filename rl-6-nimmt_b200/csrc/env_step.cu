@@ -77,13 +77,21 @@ k_step(StateView s, const uint8_t* __restrict__ actions_in, uint8_t* __restrict_
 #define NIMMT_STEP_STAGES_SMALL 3
 #endif
 #ifndef NIMMT_STEP_STAGES_LARGE
-#define NIMMT_STEP_STAGES_LARGE 3
+#define NIMMT_STEP_STAGES_LARGE 2
 #endif
+#ifndef NIMMT_STEP_STAGES_SMALL_DEEP
+#define NIMMT_STEP_STAGES_SMALL_DEEP 4
+#endif
+// Measured on the B200 (profiles/r02_step_shapes.txt): P = 4 at 2^20 games W8S3 24.1 us, W8S4 24.4, W16S2 26.4, W6S3 24.0, W4S3
+// 24.4; at 2^24 games W8S3 343 us, W8S4 326, W16S2 326; P = 10 at 2^20 / 2^24: W4S3 48.3 / 686, W4S2 47.7 / 662, W6S2 50.7 / 726.
+// A deeper pipeline pays once the batch is far beyond one wave of blocks, so the stage count is chosen per launch.
 template <int P>
 struct StepShape {
     static constexpr int kWarps = P <= 5 ? NIMMT_STEP_WARPS_SMALL : NIMMT_STEP_WARPS_LARGE;
     static constexpr int kStages = P <= 5 ? NIMMT_STEP_STAGES_SMALL : NIMMT_STEP_STAGES_LARGE;
+    static constexpr int kStagesDeep = P <= 5 ? NIMMT_STEP_STAGES_SMALL_DEEP : NIMMT_STEP_STAGES_LARGE;   // batches >= kDeepTiles tiles
 };
+constexpr int64_t kDeepTiles = 1 << 17;   // 2^22 games
 
 template <int P, int W, bool kChoice = false, bool kPacked = false>
 struct StageLayout {
@@ -110,12 +118,12 @@ __host__ __device__ constexpr uint32_t stage_stride_many(int turns) {
 
 // kPacked: the compact transfer format (step_tile.cuh): `actions` holds 4-bit hand slots, and `rewards` receives ONE bit-packed
 // record per game (bull heads, done, illegal) — staged in shared memory by the lanes and bulk-stored by the producer.
-template <int P, bool kRandom, bool kChoice = false, bool kMany = false, bool kPacked = false>
+template <int P, bool kRandom, bool kChoice = false, bool kMany = false, bool kPacked = false, int S = StepShape<P>::kStages>
 __global__ void __launch_bounds__((StepShape<P>::kWarps + 1) * 32)
 k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restrict__ actions_out, int8_t* __restrict__ rewards,
              uint8_t* __restrict__ done, uint8_t* __restrict__ illegal, int num_tiles, uint64_t seed, uint32_t turn, uint64_t game0,
              const uint8_t* __restrict__ rows = nullptr, int turns = 1) {
-    constexpr int W = StepShape<P>::kWarps, S = StepShape<P>::kStages;
+    constexpr int W = StepShape<P>::kWarps;
     using L = TileLayout<P>;
     using G = StageLayout<P, W, kChoice, kPacked>;
     static_assert(!(kMany && kChoice), "the multi-turn launch carries no row choices");
@@ -126,6 +134,7 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
     __shared__ uint64_t full[S], computed[S];
     __shared__ uint8_t values5[128];
     __shared__ uint4 keys_w[W * 32], keys_u[W * 32];          // each lane's row keys, indexable
+    __shared__ uint32_t sel8[kRandom ? 256 : 1];              // kRandom: the slot-selection table (handrec.cuh::rec_select_slot)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_groups = (num_tiles + W - 1) / W;
@@ -138,7 +147,8 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
         fence_barrier_init();
     }
     stage_card_values5(values5);
-    __syncthreads();   // the only block-wide barrier: value table + barrier init
+    if constexpr (kRandom) stage_select8(sel8);
+    __syncthreads();   // the only block-wide barrier: tables + barrier init
     const uint32_t full_a = smem_u32(full), computed_a = smem_u32(computed), stage_a = smem_u32(stage_smem);
 
     if (warp == W) {
@@ -208,7 +218,7 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
                 step_lane<P, kRandom, kChoice>(tile, stage_base + G::kActions + warp * L::kActBytes, lane, values5, kw, ku,
                                                reinterpret_cast<uint8_t*>(rewards) + g0 * P + lane_game * P, done + g0 + lane_game,
                                                illegal ? illegal + g0 + lane_game : nullptr, actions_out ? actions_out + g0 * P + lane_game * P : nullptr,
-                                               seed, game0 + (uint64_t)g0 + lane_game, turn, stage_base + G::kChoices + warp * L::kActBytes);
+                                               seed, game0 + (uint64_t)g0 + lane_game, turn, stage_base + G::kChoices + warp * L::kActBytes, sel8);
             } else {
                 const int64_t games = (int64_t)num_tiles * kTileGames;     // B: the stride between the turns of the per-game outputs
                 for (int t = 0; t < turns; ++t)                             // the tile never leaves shared memory between the turns
@@ -216,7 +226,7 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
                                                  reinterpret_cast<uint8_t*>(rewards) + (t * games + g0 + lane_game) * P, done + t * games + g0 + lane_game,
                                                  illegal ? illegal + t * games + g0 + lane_game : nullptr,
                                                  actions_out ? actions_out + (t * games + g0 + lane_game) * P : nullptr, seed,
-                                                 game0 + (uint64_t)g0 + lane_game, turn + (uint32_t)t);
+                                                 game0 + (uint64_t)g0 + lane_game, turn + (uint32_t)t, nullptr, sel8);
             }
             fence_async_smem();   // make this lane's shared-memory writes visible to the TMA engine
         }
@@ -227,22 +237,33 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
 }
 
 // kRandom = false: actions is the tape to play; true: actions (may be NULL) receives the cards drawn in the kernel.
+template <int P, bool kRandom, bool kChoice, bool kPacked, int S>
+static void launch_step_tiles(const StateView& s, uint8_t* actions, int8_t* rewards, uint8_t* done, uint8_t* illegal, uint64_t seed, uint32_t turn,
+                              uint64_t game0, cudaStream_t st, const uint8_t* rows, int64_t num_tiles) {
+    constexpr int W = StepShape<P>::kWarps;
+    constexpr int kSmem = S * StageLayout<P, W, kChoice, kPacked>::kStride;
+    constexpr int kThreads = (W + 1) * 32;
+    static int occ_cache[kMaxDevices];   // per device: the shared-memory opt-in and the occupancy are device properties
+    const int blocks_per_sm = blocks_per_sm_cached(k_step_tiles<P, kRandom, kChoice, false, kPacked, S>, kThreads, kSmem, occ_cache);
+    const int num_sms = device_sms(current_device());
+    // persistent grid: one resident wave; block b walks groups b, b + #blocks, ...
+    const int64_t groups = (num_tiles + W - 1) / W;
+    const unsigned blocks = (unsigned)min(groups, (int64_t)num_sms * blocks_per_sm);
+    k_step_tiles<P, kRandom, kChoice, false, kPacked, S><<<blocks, kThreads, kSmem, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal,
+                                                                                         (int)num_tiles, seed, turn, game0, rows);
+}
+
+// kRandom = false: actions is the tape to play; true: actions (may be NULL) receives the cards drawn in the kernel.
 template <int P, bool kRandom, bool kChoice = false, bool kPacked = false>
 static int launch_step(const StateView& s, uint8_t* actions, int8_t* rewards, uint8_t* done, uint8_t* illegal, uint64_t seed, uint32_t turn,
                        uint64_t game0, cudaStream_t st, const uint8_t* rows = nullptr) {
-    constexpr int W = StepShape<P>::kWarps, S = StepShape<P>::kStages;
-    constexpr int kSmem = S * StageLayout<P, W, kChoice, kPacked>::kStride;
-    constexpr int kThreads = (W + 1) * 32;
     const int64_t num_tiles = s.B / kTileGames;
     if (num_tiles > 0) {
-        static int occ_cache[kMaxDevices];   // per device: the shared-memory opt-in and the occupancy are device properties
-        const int blocks_per_sm = blocks_per_sm_cached(k_step_tiles<P, kRandom, kChoice, false, kPacked>, kThreads, kSmem, occ_cache);
-        const int num_sms = device_sms(current_device());
-        // persistent grid: one resident wave; block b walks groups b, b + #blocks, ...
-        const int64_t groups = (num_tiles + W - 1) / W;
-        const unsigned blocks = (unsigned)min(groups, (int64_t)num_sms * blocks_per_sm);
-        k_step_tiles<P, kRandom, kChoice, false, kPacked><<<blocks, kThreads, kSmem, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal,
-                                                                                          (int)num_tiles, seed, turn, game0, rows);
+        constexpr int S0 = StepShape<P>::kStages, S1 = StepShape<P>::kStagesDeep;
+        if (S1 != S0 && !kChoice && !kPacked && num_tiles >= kDeepTiles)
+            launch_step_tiles<P, kRandom, false, false, S1>(s, actions, rewards, done, illegal, seed, turn, game0, st, rows, num_tiles);
+        else
+            launch_step_tiles<P, kRandom, kChoice, kPacked, S0>(s, actions, rewards, done, illegal, seed, turn, game0, st, rows, num_tiles);
     }
     const int64_t tail0 = num_tiles * kTileGames;
     if (tail0 < s.B) {   // ragged tail (< 32 games): plain loads
@@ -278,12 +299,15 @@ static int launch_step_many(const StateView& s, uint8_t* actions, int8_t* reward
 template <int P>
 __global__ void __launch_bounds__(kStepThreads)
 k_random_actions(StateView s, uint8_t* __restrict__ actions, uint64_t seed, uint32_t turn, uint64_t game0) {
+    __shared__ uint32_t sel8[256];
+    stage_select8(sel8);
     const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
+    HandRec hand[P];
+    if (g < s.B) load_hands<P>(s, g, hand);   // the loads fly while the table is staged
+    __syncthreads();
     if (g >= s.B) return;
-    GameRec<P> gm;
-    load_hands<P>(s, g, gm.hand);
     int act[P];
-    random_actions_game<P>(gm, seed, game0 + (uint64_t)g, turn, act);
+    random_actions_rec<P>(hand, sel8, seed, game0 + (uint64_t)g, turn, act);
     store_bytes<P>(actions, g, act);
 }
 

@@ -59,6 +59,25 @@ NIMMT_HD uint32_t rec_card(const HandRec& h, int slot) {
     return slot < 8 ? low : high;
 }
 
+// k-th (0-based) UNPLAYED slot of a hand, in slot order (= the k-th smallest card in hand), k < rec_count: one table look-up for
+// slots 0..7 (sel8[m] lists the positions of m's set bits, 3 bits each) and two bit tests for slots 8 and 9 — a fifth of the
+// instructions of a popcount bisection.  `sel8` = the 256-word table (shared memory on the device: every lane indexes its own entry).
+__device__ __constant__ uint32_t c_select8[256] = {
+#include "select8_table.inc"
+};
+static const uint32_t h_select8[256] = {
+#include "select8_table.inc"
+};
+__device__ __forceinline__ void stage_select8(uint32_t* smem) {
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) smem[i] = c_select8[i];
+}
+NIMMT_HD uint32_t rec_select_slot(const uint32_t* sel8, uint32_t meta, uint32_t k) {
+    const uint32_t avail8 = (~meta >> 16) & 0xFFu, n8 = (uint32_t)popc32(avail8);
+    const uint32_t low = (sel8[avail8] >> (3u * k)) & 7u;            // garbage when k >= n8: not selected below
+    const uint32_t high = (k == n8 && !(meta & 0x80u)) ? 8u : 9u;    // slot 8 if it is the next unplayed one, else slot 9
+    return k < n8 ? low : high;
+}
+
 // The same for a slot known only at run time, by byte permutes instead of variable shifts (slot < 10).
 NIMMT_HD uint32_t rec_card_dyn(const HandRec& h, uint32_t slot) {
     const uint32_t low = byte_perm(h.lo.x, h.lo.y, slot & 7u), high = byte_perm(h.meta, 0u, slot & 1u);

@@ -285,6 +285,20 @@ NIMMT_HD int hand_count(const HandRec& h) { return rec_count(h); }
 NIMMT_HD uint32_t hand_select(const uint4& h, uint32_t k) { return mask_select(h, k); }
 NIMMT_HD uint32_t hand_select(const HandRec& h, uint32_t k) { return rec_select(h, k); }
 
+// The stored form with the slot-selection table (handrec.cuh::rec_select_slot): what the kernels run.
+template <int P>
+NIMMT_HD void random_actions_rec(const HandRec (&hand)[P], const uint32_t* sel8, uint64_t seed, uint64_t game_id, uint32_t turn, int (&act)[P]) {
+    Philox rng(seed, game_id, /*stream=*/0x61637400u + turn, 0);
+    uint4 r = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        if ((p & 3) == 0) r = rng.next<7>();
+        const uint32_t word = (p & 3) == 0 ? r.x : (p & 3) == 1 ? r.y : (p & 3) == 2 ? r.z : r.w;
+        const uint32_t n = (uint32_t)rec_count(hand[p]);
+        act[p] = n ? (int)rec_card_dyn(hand[p], rec_select_slot(sel8, hand[p].meta, below(word, n))) : 255;
+    }
+}
+
 template <int P, class G>
 NIMMT_HD void random_actions_game(const G& g, uint64_t seed, uint64_t game_id, uint32_t turn, int (&act)[P]) {
     Philox rng(seed, game_id, /*stream=*/0x61637400u + turn, 0);

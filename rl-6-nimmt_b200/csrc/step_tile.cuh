@@ -36,7 +36,7 @@ constexpr int packed_result_bytes() { return (5 * P + 2 + 7) / 8; }
 template <int P, bool kRandom, bool kChoice = false, bool kPacked = false>
 NIMMT_HD void step_lane(uint8_t* tile, const uint8_t* acts, int lane, const uint8_t* values5, uint32_t* keys_w, uint32_t* keys_u,
                                           uint8_t* rew_out, uint8_t* done_out, uint8_t* illegal_out, uint8_t* act_out, uint64_t seed,
-                                          uint64_t game_id, uint32_t turn, const uint8_t* rows = nullptr) {
+                                          uint64_t game_id, uint32_t turn, const uint8_t* rows = nullptr, const uint32_t* sel8 = nullptr) {
     using L = TileLayout<P>;
     const uint2* cards0 = reinterpret_cast<const uint2*>(tile) + lane;              // + p * kTileGames
     uint32_t* meta0 = reinterpret_cast<uint32_t*>(tile + L::kMeta) + lane;           // + p * kTileGames
@@ -57,8 +57,8 @@ NIMMT_HD void step_lane(uint8_t* tile, const uint8_t* acts, int lane, const uint
             h.lo = cards0[p * kTileGames];
             h.meta = meta0[p * kTileGames];
             const uint32_t n = (uint32_t)rec_count(h);
-            const uint32_t slot = select_bit32(~rec_empties(h.meta) & kSlotBits, below(word, n ? n : 1u));
-            act[p] = n ? rec_card(h, (int)slot) : 255u;
+            const uint32_t slot = rec_select_slot(sel8, h.meta, below(word, n ? n : 1u));   // the k-th unplayed slot: one table look-up
+            act[p] = n ? rec_card_dyn(h, slot) : 255u;
             meta[p] = h.meta | (n ? rec_slot_mask(slot) : 0u);
             legal = legal && n != 0u;                      // an empty hand "plays" 255: rejected like any illegal card
         }

@@ -161,7 +161,7 @@ static void replay_tiles(int n, int turns, const int8_t* rows0, const int8_t* ha
                 alignas(16) uint32_t kw[4], ku[4];
                 uint8_t rew[P + 8], dn = 0, ill = 0, drawn[P];
                 step_lane<P, kRandom, kChoice, kPacked>(tile, acts, lane, values5, kw, ku, rew, &dn, &ill, kRandom ? drawn : nullptr, seed,
-                                                        game0 + (uint64_t)(first + lane), (uint32_t)t, chosen);
+                                                        game0 + (uint64_t)(first + lane), (uint32_t)t, chosen, h_select8);
                 if (kPacked) {   // unpack the bit record: 5 bits of bull heads per player, done, illegal
                     uint64_t rec = 0;
                     for (int b = 0; b < packed_result_bytes<P>(); ++b) rec |= (uint64_t)rew[b] << (8 * b);
