@@ -62,14 +62,15 @@ NIMMT_HD uint32_t rec_card(const HandRec& h, int slot) {
 // k-th (0-based) UNPLAYED slot of a hand, in slot order (= the k-th smallest card in hand), k < rec_count: one table look-up for
 // slots 0..7 (sel8[m] lists the positions of m's set bits, 3 bits each) and two bit tests for slots 8 and 9 — a fifth of the
 // instructions of a popcount bisection.  `sel8` = the 256-word table (shared memory on the device: every lane indexes its own entry).
-__device__ __constant__ uint32_t c_select8[256] = {
+// (global memory, not __constant__: the staging loop reads 32 different words per warp, which the constant cache would serialise)
+__device__ const uint32_t d_select8[256] = {
 #include "select8_table.inc"
 };
 static const uint32_t h_select8[256] = {
 #include "select8_table.inc"
 };
 __device__ __forceinline__ void stage_select8(uint32_t* smem) {
-    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) smem[i] = c_select8[i];
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) smem[i] = d_select8[i];
 }
 NIMMT_HD uint32_t rec_select_slot(const uint32_t* sel8, uint32_t meta, uint32_t k) {
     const uint32_t avail8 = (~meta >> 16) & 0xFFu, n8 = (uint32_t)popc32(avail8);
