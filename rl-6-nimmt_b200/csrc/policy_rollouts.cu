@@ -165,7 +165,9 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
         }
         int outcome = 0, first_index = -1;
         rk = rk_root;
+        pc.mark(11);
         __syncthreads();
+        pc.mark(12);
         {   // Resolve the shuffle without running it: draw i takes what sits at position k_i after swaps 0..i-1.  Position p
             // holds its original card unless an earlier swap j (the latest with k_j == p) moved position j's content there,
             // and so on back — a walk over j = i-1 .. 0 that every row does for its own draw in parallel, instead of a chain
@@ -177,6 +179,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
             if (opp && slot < root_n) {
                 v = (int)ts.deck[fisher_yates_source<(P - 1) * kHand>(ts.draw, i)];
             }
+            pc.mark(13);
             int rank = 0;
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) rank += __shfl_sync(kFull, v, gbase + s) < v;
@@ -234,6 +237,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
                     if (playing && player == 0) pick = j % h;
                 }
             }
+            pc.mark(14);
             // ---- every other move: the largest perturbed logit among the decision's cards ----
             {
                 // order-preserving integer image of the float, hand slot in the low four bits (ties: lowest slot)
@@ -245,6 +249,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
                 for (int s = 0; s < kSlots; ++s) winner = max(winner, __shfl_sync(kFull, key, gbase + s));
                 if (pick < 0) pick = 15 - (winner & 15);
             }
+            pc.mark(15);
             // ---- hand.remove(card): the lanes behind the pick shift down by one ----
             const int chosen = __shfl_sync(kFull, card, gbase + max(pick, 0));
             const int next = __shfl_sync(kFull, card, (lane + 1) & 31);
@@ -292,8 +297,9 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
 
 #ifdef NIMMT_PHASE_CLOCKS
     {
-        static const char* const names[] = {"features", "sync+fence", "mma1 wait", "epilogue1", "sync", "mma2 wait", "epilogue2", "softmax", "sync", "env step", "deal+sort"};
-        pc.print(names, 11);
+        static const char* const names[] = {"features", "sync+fence", "mma1 wait", "epilogue1", "sync", "mma2 wait", "epilogue2", "hand update", "sync", "env step",
+                                            "rank sort", "restore+draw", "deal sync", "fy walk", "root rule", "argmax"};
+        pc.print(names, 16);
     }
 #endif
     // ---- results ----
