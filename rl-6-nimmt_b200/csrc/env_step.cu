@@ -1,5 +1,7 @@
 // env_step.cu — batched env.step, random actions, and the two fused (SechsNimmtEnv.step, env.py:64-77;
 // DrunkHamster.forward, agents/random.py:8-10).  One thread per game; HBM-bandwidth bound.
+#include <cstdlib>
+
 #include "abi_common.cuh"
 #include "step_tile.cuh"
 #include "tma.cuh"
@@ -138,6 +140,10 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_groups = (num_tiles + W - 1) / W;
+    // Programmatic dependent launch: this grid may have been launched while the previous kernel of the stream was still draining
+    // (launch_step_tiles sets the attribute), and lets the next one do the same.  Everything up to griddepcontrol.wait — barrier
+    // initialisation, the tables — touches no memory another kernel writes and overlaps the previous kernel's tail.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int i = 0; i < S; ++i) {
@@ -149,6 +155,7 @@ k_step_tiles(StateView s, const uint8_t* __restrict__ actions, uint8_t* __restri
     stage_card_values5(values5);
     if constexpr (kRandom) stage_select8(sel8);
     __syncthreads();   // the only block-wide barrier: tables + barrier init
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous kernel's writes (this state, the outputs' last readers) are complete and visible
     const uint32_t full_a = smem_u32(full), computed_a = smem_u32(computed), stage_a = smem_u32(stage_smem);
 
     if (warp == W) {
@@ -249,8 +256,21 @@ static void launch_step_tiles(const StateView& s, uint8_t* actions, int8_t* rewa
     // persistent grid: one resident wave; block b walks groups b, b + #blocks, ...
     const int64_t groups = (num_tiles + W - 1) / W;
     const unsigned blocks = (unsigned)min(groups, (int64_t)num_sms * blocks_per_sm);
-    k_step_tiles<P, kRandom, kChoice, false, kPacked, S><<<blocks, kThreads, kSmem, st>>>(s, actions, kRandom ? actions : nullptr, rewards, done, illegal,
-                                                                                         (int)num_tiles, seed, turn, game0, rows);
+    // launched with programmatic stream serialisation: the grid may start its prologue while the previous kernel of the stream
+    // drains (it waits at griddepcontrol.wait before touching memory).  NIMMT_STEP_PDL=0 launches it the plain way.
+    static const bool pdl = [] { const char* v = getenv("NIMMT_STEP_PDL"); return !(v && v[0] == '0'); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_step_tiles<P, kRandom, kChoice, false, kPacked, S>, s, (const uint8_t*)actions, kRandom ? actions : (uint8_t*)nullptr, rewards, done,
+                       illegal, (int)num_tiles, seed, turn, game0, rows, 1);
 }
 
 // kRandom = false: actions is the tape to play; true: actions (may be NULL) receives the cards drawn in the kernel.
