@@ -311,6 +311,29 @@ def run_ours(args):
     assert sum(int(e.illegal.any()) for e in envs) == 0
     kstep_ms, kdeal_ms = statistics.median(kstep_runs), statistics.median(kdeal_runs)
 
+    # ---- also: the same 40-step cycle with the re-deals issued on a side stream, so that the deal of one batch (instruction-bound)
+    # runs under the other batches' steps (memory-bound).  Every batch's own order deal -> ten steps is kept. ----
+    side = torch.cuda.Stream(device=dev)
+    g_side = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_side):
+        cap = torch.cuda.current_stream(dev)
+        side.wait_stream(cap)
+        dealt = []
+        with torch.cuda.stream(side):
+            for env in envs:
+                env.reset(seed=env.seed)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                dealt.append(ev)
+        for i in range(CYCLE):
+            if i < NSETS:
+                cap.wait_event(dealt[i])
+            envs[i % NSETS].step(tapes[i % NSETS][i // NSETS])
+        cap.wait_stream(side)
+    g_side.replay()
+    side_ms = statistics.median(event_ms(g_side.replay) for _ in range(7)) / CYCLE
+    assert sum(int(e.illegal.any()) for e in envs) == 0
+
     # ---- step + observe ("report step-only and step+observe separately"; the reference rebuilds all P observations
     # inside every step, env.py:73): the same cycle with k_observe after every step, int8 and fp32 observations ----
     step_obs = {}
@@ -525,7 +548,7 @@ def run_ours(args):
     # ---- BASELINE configs[4]: ten-player max-table sweep, the games split evenly over the ranks (weak per-rank timing, max over ranks) ----
     sweep = []
     free_bytes = torch.cuda.mem_get_info(dev)[0]
-    del envs, tapes, h_actions, h_out, h_slots, h_packed, streams, g_cycle, g_rem, g_fin, g_deal, g_steps, g2, g3, session
+    del envs, tapes, h_actions, h_out, h_slots, h_packed, streams, g_cycle, g_rem, g_fin, g_deal, g_steps, g_side, g2, g3, session
     torch.cuda.empty_cache()
     for lg in args.sweep_log2:
         total_games = 1 << lg
@@ -589,6 +612,8 @@ def run_ours(args):
         "gpu_launches": timed_launches,
         "clocks": clocks,
         "also": {"k_random_actions_ms": ra_ms, "k_deal_ms": kdeal_ms,
+                 "env_steps_per_sec_redeal_on_side_stream": world * B / (side_ms * 1e-3),
+                 "redeal_on_side_stream_note": "the timed 40-step cycle with the 4 re-deals issued on a second stream (each batch still deal -> ten steps in order): the instruction-bound deal runs under the other batches' memory-bound steps; `value` keeps everything on one stream",
                  "fused_random_play_env_steps_per_sec": world * B / (fused_ms * 1e-3),
                  "fused_note": "k_step_tiles<4,true>: actions drawn in-kernel (DrunkHamster for every seat), + k_deal every 10th visit; max over ranks",
                  "step_plus_observe_i8": step_obs["i8"], "step_plus_observe_f32": step_obs["f32"],
