@@ -308,43 +308,12 @@ struct RowKeys {
     }
 };
 
-// The same placement on row keys that live in indexable memory (this thread's four w and four u words, each group
-// 16-byte aligned: shared memory on the device).  The four rows are read with two 128-bit loads and the one row that
-// changes is written with two 32-bit stores, instead of the eight predicated selects (and four compares) that keeping the
-// rows in registers costs — the kernels that call this are bound by the ALU pipe, not by the load/store pipe.
-// STRIDE = 1: the four words of a group are contiguous (one 128-bit load each).  STRIDE = n: row r of this thread sits
-// at word r * n — the threads of a block interleave their groups, so that every load and, above all, the store to the
-// data-dependent row r is free of bank conflicts.
-template <int STRIDE = 1>
-NIMMT_HD int place_indexed(int* w, int* u, int card, int value, int& row, uint32_t& keep_len) {
-    int4 W, U;
-    if constexpr (STRIDE == 1) {
-        W = *reinterpret_cast<const int4*>(w);
-        U = *reinterpret_cast<const int4*>(u);
-    } else {
-        W = make_int4(w[0], w[STRIDE], w[2 * STRIDE], w[3 * STRIDE]);
-        U = make_int4(u[0], u[STRIDE], u[2 * STRIDE], u[3 * STRIDE]);
-    }
-    const int ck = card << 10;
-    const uint32_t d0 = (uint32_t)(ck - W.x), d1 = (uint32_t)(ck - W.y), d2 = (uint32_t)(ck - W.z), d3 = (uint32_t)(ck - W.w);
-    const uint32_t dmin = umin32(umin32(d0, d1), umin32(d2, d3));
-    const int best = ck - (int)dmin;
-    const int cheapest = imin(imin(U.x, U.y), imin(U.z, U.w));
-    const bool under = dmin > (uint32_t)ck;   // card below every top
-    const int r = (under ? cheapest : best) & 3;
-    const uint32_t len = ((uint32_t)best >> 2) & 7u;  // garbage when under; take is true then
-    const uint32_t sum = under ? (uint32_t)cheapest >> 2 : ((uint32_t)best >> 5) & 31u;
-    const bool take = under || len == 5u;
-    keep_len = take ? 0u : len;
-    const uint32_t new_sum = (take ? 0u : sum) + (uint32_t)value;
-    w[r * STRIDE] = ck | (int)((new_sum << 5) | ((keep_len + 1u) << 2)) | r;
-    u[r * STRIDE] = (int)(new_sum << 2) | r;
-    row = r;
-    return take ? (int)sum : 0;
-}
-
 // ----------------------------------------------------------------------------------------------
-// Placement, third form (the throughput kernels: k_step_tiles, k_mcs_rollouts).  Same rule as RowKeys::place, with the bit
+// Placement on row keys that live in INDEXABLE memory (this thread's four w and four u words, each group 16-byte aligned: shared
+// memory on the device; STRIDE = n interleaves the threads of a block, row r of this thread at word r * n, so that the store to
+// the data-dependent row is free of bank conflicts) — the throughput kernels k_step_tiles and k_mcs_rollouts.  The four rows are
+// read with two 128-bit loads and the one row that changes is written with two 32-bit stores, instead of the eight predicated
+// selects (and four compares) that keeping the rows in registers costs.  Same rule as RowKeys::place, with the bit
 // fields arranged so that almost nothing has to be shifted:
 //   W[r] = top << 10 | sum << 5 | len << 2 | r        as before
 //   U[r] =             sum << 5            | r        the undercut key, its fields ALIGNED with W's
