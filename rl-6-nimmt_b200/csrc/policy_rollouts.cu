@@ -160,7 +160,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
             const int i = player * kSlots + slot;
             if (i < need) {
                 Philox rng(seed, rollout_id, 0x6465616cu, (uint32_t)i);
-                ts.draw[i] = (uint8_t)(i + (int)below(rng.next().x, (uint32_t)(n_avail - i)));   // swap target k_i of Fisher-Yates step i
+                ts.draw[i] = (uint8_t)(i + (int)below(rng.next<7>().x, (uint32_t)(n_avail - i)));   // swap target k_i of Fisher-Yates step i
             }
         }
         int outcome = 0, first_index = -1;
@@ -214,7 +214,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
             float gumbel = 0.0f;
             const float logit = mlp_tile(smem + kSmemBlob, gbuf, tmem_base, &bar, phase, threadIdx.x, 0, pc, [&](uint32_t token) {
                 Philox rng(seed, rollout_id, (0x73616d70u + (uint32_t)turn) ^ token, (uint32_t)(player * 16 + slot));
-                const float u = ((float)(rng.next().x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // in (0, 1)
+                const float u = ((float)(rng.next<7>().x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // in (0, 1)
                 gumbel = -__logf(-__logf(u));
                 pin_result(gumbel);
             });
