@@ -50,6 +50,17 @@ class Box:
         return f"Box({self.low}, {self.high}, {self.shape}, {self.dtype})"
 
 
+def unpack_packed_results(packed, num_players):
+    """The bit records of nimmt_step_packed (uint8 [B, ceil((5P+2)/8)], little-endian: 5 bits of bull heads per player, then done,
+    then illegal) -> (rewards int8 [B,P], done bool [B], illegal bool [B]).  Works on any device."""
+    P = num_players
+    rec = torch.zeros(packed.shape[0], dtype=torch.int64, device=packed.device)
+    for b in range(packed.shape[1]):
+        rec |= packed[:, b].to(torch.int64) << (8 * b)
+    rewards = torch.stack([-((rec >> (5 * p)) & 31) for p in range(P)], dim=1).to(torch.int8)
+    return rewards, ((rec >> (5 * P)) & 1).bool(), ((rec >> (5 * P + 1)) & 1).bool()
+
+
 def _as_device(x, dtype, device):
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=dtype).contiguous()
@@ -217,12 +228,7 @@ class BatchedSechsNimmtEnv:
 
     def unpack_results(self, packed):
         """uint8 [B, ceil((5P+2)/8)] -> (rewards int8 [B,P], done bool [B], illegal bool [B])."""
-        P = self.num_players
-        rec = torch.zeros(packed.shape[0], dtype=torch.int64, device=packed.device)
-        for b in range(packed.shape[1]):
-            rec |= packed[:, b].to(torch.int64) << (8 * b)
-        rewards = torch.stack([-((rec >> (5 * p)) & 31) for p in range(P)], dim=1).to(torch.int8)
-        return rewards, ((rec >> (5 * P)) & 1).bool(), ((rec >> (5 * P + 1)) & 1).bool()
+        return unpack_packed_results(packed, self.num_players)
 
     def step_packed(self, slots, out=None):
         """:meth:`step` in the packed transfer format: slots uint8 [B, ceil(P/2)] device tensor (:meth:`pack_slots`) ->
