@@ -1,5 +1,6 @@
-// env_step.cu — batched env.step, random actions, and the two fused (SechsNimmtEnv.step, env.py:64-77;
-// DrunkHamster.forward, agents/random.py:8-10).  One thread per game; HBM-bandwidth bound.
+// env_step.cu — batched env.step (SechsNimmtEnv.step, env.py:64-77), uniformly random actions (DrunkHamster.forward,
+// agents/random.py:8-10) and the two fused; the multi-turn, free-row-choice and packed-transfer variants of the step.
+// One game per lane; the throughput kernel (k_step_tiles) is warp-specialised and HBM-bandwidth bound.
 #include <cstdlib>
 
 #include "abi_common.cuh"

@@ -367,7 +367,7 @@ struct Board {
 
     // The stored 24-byte row record is slot-major: byte 4 j + r = j-th card (oldest first) of row r
     // for j = 0..4, byte 20 + r = meta of row r (len | sum << 3).  A placement touches exactly one
-    // byte of it (plus the meta bytes), which is what lets k_step_smem update it in place.
+    // byte of it (plus the meta bytes), which is what lets k_step_tiles update it in place.
     // q0 / q1 / q2 are its three little-endian 64-bit words.
     NIMMT_HD void unpack(uint64_t q0, uint64_t q1, uint64_t q2) {
         const uint32_t slot[5] = {(uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)q1, (uint32_t)(q1 >> 32), (uint32_t)q2};
@@ -403,7 +403,7 @@ struct Board {
         uint32_t keep_len;
         const int penalty = k.place(card, value, r, keep_len, choice);
         // write the one slot the card lands in; slots at index >= len keep whatever they held
-        // (they are unspecified in the stored record: k_step_smem writes a single byte too)
+        // (they are unspecified in the stored record: k_step_tiles writes a single byte too)
         const uint32_t shift = 8u * keep_len;
         const uint64_t clear = ~(0xFFull << shift), put = (uint64_t)(uint32_t)card << shift;
 #pragma unroll

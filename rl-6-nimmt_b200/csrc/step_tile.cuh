@@ -21,7 +21,8 @@ struct TileLayout {
 //   tile     the tile record (cards | meta | rows) in shared memory
 //   acts     the tile's action bytes in shared memory (kRandom: unused)
 //   keys_w/u this lane's row keys (game.cuh::place_v3), 16-byte aligned
-// Returns the game's rewards packed one byte per player (P <= 4: one word; larger P: stored through `rew_out`).
+//   rew_out / done_out / illegal_out / act_out   where this game's P reward bytes, its flags and (kRandom) its drawn cards go
+//            (global memory on the device: a warp's lanes write neighbouring addresses)
 //   kChoice  free-row-choice mode: `rows` holds, like `acts`, one byte per (game, player) — the row that player takes if their
 //            card undercuts every row (0..3; anything else rejects the step like an illegal card)
 //   kPacked  the compact transfer format for hosts on the far side of PCIe (nimmt_step_packed): `acts` holds one 4-bit HAND SLOT
