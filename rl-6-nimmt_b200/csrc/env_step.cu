@@ -317,12 +317,14 @@ static int launch_step_many(const StateView& s, uint8_t* actions, int8_t* reward
 // ------------------------------------------------------------------------------------------
 // k_random_actions — DrunkHamster.forward for every (game, player) (agents/random.py:8-10).
 // ------------------------------------------------------------------------------------------
+constexpr int kActionThreads = 256;   // = the entries of the slot-selection table: every thread stages exactly one
+
 template <int P>
-__global__ void __launch_bounds__(kStepThreads)
+__global__ void __launch_bounds__(kActionThreads)
 k_random_actions(StateView s, uint8_t* __restrict__ actions, uint64_t seed, uint32_t turn, uint64_t game0) {
     __shared__ uint32_t sel8[256];
-    stage_select8(sel8);
-    const int64_t g = (int64_t)blockIdx.x * kStepThreads + threadIdx.x;
+    sel8[threadIdx.x] = d_select8[threadIdx.x];
+    const int64_t g = (int64_t)blockIdx.x * kActionThreads + threadIdx.x;
     HandRec hand[P];
     if (g < s.B) load_hands<P>(s, g, hand);   // the loads fly while the table is staged
     __syncthreads();
@@ -455,7 +457,7 @@ int nimmt_random_actions(const void* state, uint8_t* actions, int64_t B, int num
     if (!aligned16(actions)) return NIMMT_E_ALIGN;
     if (B == 0) return NIMMT_OK;
     StateView s(const_cast<void*>(state), B, num_players);
-    NIMMT_DISPATCH_P(num_players, k_random_actions<P><<<blocks_for(B, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
+    NIMMT_DISPATCH_P(num_players, k_random_actions<P><<<blocks_for(B, kActionThreads), kActionThreads, 0, (cudaStream_t)stream>>>(
                                       s, actions, seed, turn, game0));
     return check_launch();
 }
