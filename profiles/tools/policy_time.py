@@ -35,3 +35,27 @@ for name, mode in (("puct", 0), ("policy", 1)):
     print(f"k_policy_rollouts<{P}> mode={name}: {ms:.3f} ms per 256 x 200 rollouts = {256 * 200 / ms * 1e3:.3e} rollouts/s, {ms * 1e3 / 200 / 10:.2f} us per turn")
 ms = timed(lambda: PL.policy_probs(obs, blob), 5)
 print(f"k_policy_probs: {ms:.3f} ms per {obs.shape[0]} decisions = {obs.shape[0] / ms * 1e3:.3e} decisions/s")
+
+# the state-only 47-100-100-104 nets of the model-free agents on the same tile (k_masked_probs), against PyTorch on the device
+from torch import nn
+
+
+class _MaskedNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.latent_net = nn.Sequential(nn.Linear(47, 100), nn.ReLU(), nn.Linear(100, 100), nn.ReLU())
+        self.head_nets = nn.ModuleList([nn.Sequential(nn.Linear(100, 104))])
+
+    def forward(self, x):
+        h = self.latent_net(x)
+        return [head(h) for head in self.head_nets]
+
+
+mnet = _MaskedNet().cuda()
+mblob = PL.pack_masked_weights(mnet)
+ms = timed(lambda: PL.masked_probs(obs, mblob), 5)
+print(f"k_masked_probs: {ms:.3f} ms per {obs.shape[0]} decisions = {obs.shape[0] / ms * 1e3:.3e} decisions/s, "
+      f"{obs.shape[0] * 2 * (47 * 100 + 100 * 100 + 100 * 104) / ms * 1e3 / 1e12:.0f} TFLOP/s (un-padded)")
+with torch.no_grad():
+    ms = timed(lambda: PL.masked_card_probs(mnet, obs), 3)
+print(f"the same net in PyTorch (fp32 cuBLAS) on the device: {ms:.3f} ms")
