@@ -8,8 +8,9 @@
 //   layer 2: [128 x 112] x [112 x 112]   b2 rides on the constant-1 units 100, 101 of layer 1
 //   layer 3: [128 x 112] x [112 x 112]   one output column per card (104 of 112 used); b3 rides on units 100, 101 of layer 2,
 //                                        which the packed W2 holds at the constant 1
-// all three as tcgen05.mma (kind::f16, bf16 operands in shared memory, fp32 accumulator in TMEM) issued by one thread;
-// epilogues 1 and 2 are policy_tile.cuh's TMEM -> ReLU -> bf16 -> next layer's A operand; epilogue 3 stages each row's 104
+// all three as tcgen05.mma (kind::f16, fp32 accumulator in TMEM) issued by one thread; layer 1 reads both operands from shared
+// memory, layers 2 and 3 read A from TENSOR memory: epilogues 1 and 2 are policy_tile.cuh's relu_to_operand (TMEM -> ReLU ->
+// bf16 pairs -> TMEM), so the activations never pass through shared memory; epilogue 3 stages each row's 104
 // logits in shared memory, and the row's own thread gathers the <= 10 cards of its hand and normalises them.
 #include "policy_tile.cuh"
 
@@ -18,23 +19,11 @@ namespace nimmt {
 constexpr uint32_t kMOffW1 = 0, kMOffW2 = kMOffW1 + kW1Bytes, kMOffW3 = kMOffW2 + kW2Bytes;
 constexpr uint32_t kMaskedBlobBytes = kMOffW3 + kW2Bytes;                        // 64512
 constexpr int kCardsOut = 104, kLogitStride = 105;                               // odd stride: a warp's rows hit 32 banks
-constexpr uint32_t kMSmemBlob = 0, kMSmemA1 = (kMaskedBlobBytes + 127) / 128 * 128, kMSmemA2 = kMSmemA1 + kA1Bytes;
-constexpr uint32_t kMSmemObs = kMSmemA2 + kA2Bytes;                              // int8 [128][47] (+ pad to words)
+constexpr uint32_t kMSmemBlob = 0, kMSmemA1 = (kMaskedBlobBytes + 127) / 128 * 128;
+constexpr uint32_t kMSmemObs = kMSmemA1 + kA1Bytes;                              // int8 [128][47] (+ pad to words)
+constexpr uint32_t kMaskedTmemCols = 256;                                        // 168 used (policy_tile.cuh::kTmemColsPerGroup)
 constexpr uint32_t kMSmemLogits = (kMSmemObs + kTileRows * kObs + 127) / 128 * 128;
 constexpr uint32_t kMaskedSmemBytes = kMSmemLogits + kTileRows * kLogitStride * 4;
-
-// TMEM -> ReLU -> bf16 -> the next layer's A operand, all 104 columns that exist (epilogue 1 of policy_tile.cuh::mlp_tile)
-__device__ __forceinline__ void relu_to_operand(uint32_t lane_taddr, uint8_t* a_row) {
-    epilogue1_chunks<0, 4>(lane_taddr, a_row);
-    epilogue1_chunks<4, 6>(lane_taddr, a_row);
-    uint32_t v[8];   // units 96..103 (100, 101 are the constant-1 units that carry the next layer's bias)
-    tmem_ld8(lane_taddr + 96, v);
-    tmem_ld_wait();
-    uint32_t packed[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) packed[i] = relu_pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-    *reinterpret_cast<uint4*>(a_row + 12 * 128) = make_uint4(packed[0], packed[1], packed[2], packed[3]);   // canon_off(row, 96, .) - canon_off(row, 0, .)
-}
 
 __global__ void __launch_bounds__(kTileRows, 1)
 k_masked_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restrict__ blob, float* __restrict__ probs, float* __restrict__ logits_out) {
@@ -49,19 +38,17 @@ k_masked_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
-    if (tid < 32) tmem_alloc(&tmem_slot, kTmemColsPerGroup);
+    if (tid < 32) tmem_alloc(&tmem_slot, kMaskedTmemCols);
     uint8_t* a1_row = smem + kMSmemA1 + canon_off(tid, 0, kInChunks);
-    uint8_t* a2_row = smem + kMSmemA2 + canon_off(tid, 0, kHidChunks);
-    // once: the constant chunks of this thread's rows (features 48..63 = 1 1 0 ..; hidden units 104..111 = 0)
+    // once: the constant chunks of this thread's row (features 48..63 = 1 1 0 ..)
     *reinterpret_cast<uint4*>(a1_row + (kBiasCol / 8) * 128) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(a1_row + (kBiasCol / 8 + 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(a2_row + (kHidPad / 8 - 1) * 128) = make_uint4(0u, 0u, 0u, 0u);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint32_t a1 = smem_u32(smem + kMSmemA1), a2 = smem_u32(smem + kMSmemA2);
+    const uint32_t a1 = smem_u32(smem + kMSmemA1);
     const uint32_t w1 = smem_u32(smem + kMOffW1), w2 = smem_u32(smem + kMOffW2), w3 = smem_u32(smem + kMOffW3);
     constexpr uint32_t idesc = umma_idesc_bf16(kTileRows, kHidPad);
     uint32_t phase = 0;
@@ -103,11 +90,11 @@ k_masked_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
         mbar_wait_mma(&bar, phase);
         phase ^= 1u;
         tc_fence_after_sync();
-        relu_to_operand(lane_taddr, a2_row);
-        // ---- layers 2 and 3: the same [128 x 112] x [112 x 112] product with different weights ----
+        relu_to_operand(lane_taddr, lane_taddr);     // in place: operand columns [0, 56) over accumulator columns already read
+        // ---- layers 2 and 3: the same [128 x 112] x [112 x 112] product with different weights, A from tensor memory
+        // (columns [0, 56)), accumulator in columns [56, 168) ----
 #pragma unroll
         for (int layer = 2; layer <= 3; ++layer) {
-            fence_async_smem();
             tc_fence_before_sync();
             __syncthreads();          // every lane's accumulator has been read and its operand row written
             if (tid == 0) {
@@ -115,26 +102,26 @@ k_masked_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
                 const uint32_t w = layer == 2 ? w2 : w3;
 #pragma unroll
                 for (int ks = 0; ks < kHidPad / 16; ++ks)
-                    umma_bf16(tmem_base, umma_desc(a2 + ks * 256, 128, kHidChunks * 128), umma_desc(w + ks * 256, 128, kHidChunks * 128), idesc, ks > 0);
+                    umma_bf16_ts(tmem_base + kTmemAcc2, tmem_base + ks * 8, umma_desc(w + ks * 256, 128, kHidChunks * 128), idesc, ks > 0);
                 umma_commit(&bar);
             }
             mbar_wait_mma(&bar, phase);
             phase ^= 1u;
             tc_fence_after_sync();
-            if (layer == 2) relu_to_operand(lane_taddr, a2_row);   // the MMAs that read the old rows have completed
+            if (layer == 2) relu_to_operand(lane_taddr + kTmemAcc2, lane_taddr);   // the MMAs that read the old operand have completed
         }
         // ---- epilogue 3: this row's 104 logits -> shared memory, then the cards in hand ----
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             uint32_t v[16];
-            tmem_ld16(lane_taddr + c * 16, v);
+            tmem_ld16(lane_taddr + kTmemAcc2 + c * 16, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) my_logits[c * 16 + i] = __uint_as_float(v[i]);
         }
         {
             uint32_t v[8];
-            tmem_ld8(lane_taddr + 96, v);
+            tmem_ld8(lane_taddr + kTmemAcc2 + 96, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 8; ++i) my_logits[96 + i] = __uint_as_float(v[i]);
@@ -165,7 +152,7 @@ k_masked_probs(const int8_t* __restrict__ obs, int64_t D, const uint8_t* __restr
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (tid < 32) tmem_dealloc(tmem_base, kTmemColsPerGroup);
+    if (tid < 32) tmem_dealloc(tmem_base, kMaskedTmemCols);
 }
 
 }  // namespace nimmt

@@ -49,6 +49,8 @@ struct TreeState {
 
 __device__ __forceinline__ float uniform01(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
 constexpr uint16_t kBf16MinusOne = 0xBF80;
+constexpr uint32_t kSearchSmemBytes = kSmemGroups + kA1Bytes;   // the weights + one layer-1 operand
+constexpr uint32_t kSearchTmemCols = 256;   // 168 used (policy_tile.cuh::kTmemColsPerGroup); allocations are powers of two
 
 template <int P>
 __global__ void __launch_bounds__(kTileRows, 1)
@@ -69,7 +71,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
-    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, kTmemColsPerGroup);
+    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, kSearchTmemCols);
     uint8_t* gbuf = smem + kSmemGroups;
     init_feature_constants(gbuf, threadIdx.x);
     tc_fence_before_sync();
@@ -217,7 +219,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
                 const float u = ((float)(rng.next<7>().x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // in (0, 1)
                 gumbel = -__logf(-__logf(u));
                 pin_result(gumbel);
-            });
+            }, [] {});
 
             // ---- player 0's first move: PUCT over the earlier outcomes, or the stratified schedule ----
             int pick = -1;
@@ -313,7 +315,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem_base, kTmemColsPerGroup);
+    if (threadIdx.x < 32) tmem_dealloc(tmem_base, kSearchTmemCols);
 }
 
 // PUCTAgent._compute_pucts / _normalize_q / the choice (agents/mcts.py:276-315) for a batch of decisions whose outcome lists are
@@ -368,8 +370,8 @@ int nimmt_policy_rollouts(const nimmt_root* roots, int num_roots, int num_player
     switch (num_players) {
 #define CASE(P_)                                                                                                             \
     case P_:                                                                                                                 \
-        cudaFuncSetAttribute(k_policy_rollouts<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)policy_smem_bytes(1));            \
-        k_policy_rollouts<P_><<<blocks, kTileRows, policy_smem_bytes(1), cs>>>(roots, num_roots, blob, n_mc, c_puct, mode, seed, st, root_probs); \
+        cudaFuncSetAttribute(k_policy_rollouts<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSearchSmemBytes);            \
+        k_policy_rollouts<P_><<<blocks, kTileRows, kSearchSmemBytes, cs>>>(roots, num_roots, blob, n_mc, c_puct, mode, seed, st, root_probs); \
         break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
 #undef CASE

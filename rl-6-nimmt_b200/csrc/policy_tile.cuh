@@ -1,12 +1,17 @@
 // policy_tile.cuh — one 128-row tile of the Alpha0.5 policy net on tcgen05 (shared by the batched
 // leaf-evaluation kernel and the policy-rollout kernel).  See policy_kernels.cu for the overview.
 //
-// Both kernels are bound by per-thread instruction latency around the MMAs, not by the MMAs, so the tile is
-// built to keep the threads' share small:
+// Both kernels are bound by what happens around the MMAs — per-thread instruction latency in the search kernel, shared-memory
+// bandwidth in the batched one (an SS-mode MMA of this shape reads 7.5 KB of operands per 56 tensor cycles, on the same
+// 128 B/clk the threads' stores use) — so the tile is built to keep both small:
 //   * biases ride in the GEMMs: features 48, 49 of every row are the constant 1 and carry b1 split into two
 //     bf16 terms (hi + lo, ~16 mantissa bits); layer 1's units 100, 101 are the constant 1 and carry b2 the
 //     same way.  Epilogue 1 is cvt.relu.bf16x2 + store; epilogue 2 is ONE fma per column, because the linear half
 //     of the ReLU head is computed by the GEMM as well (epilogue2_chunks).
+//   * layer 2's A operand never touches shared memory: epilogue 1 writes the bf16 activations back into TENSOR memory
+//     (tcgen05.st, a thread's row = its TMEM lane, two units per 32-bit column) on top of the accumulator columns it has
+//     just read, and layer 2 runs with A from TMEM (umma_bf16_ts).  Per tile that removes 28 KB of shared-memory stores, the
+//     tensor core's 28 KB read of them and the async-proxy fence between the two.
 //   * feature rows are assembled from bf16 data that is already laid out in 16-byte chunks (six vector
 //     loads and stores per row) instead of 48 scalar conversions.
 #pragma once
@@ -29,15 +34,15 @@ constexpr uint32_t kW2Bytes = (kHidPad / 8) * kHidChunks * 128;   // 25088
 constexpr uint32_t kOffW1 = 0, kOffW2 = kOffW1 + kW1Bytes, kOffW3 = kOffW2 + kW2Bytes, kOffB3 = kOffW3 + kHidPad * 4;
 constexpr uint32_t kBlobBytes = kOffB3 + 16;                      // 39888
 constexpr uint32_t kA1Bytes = (kTileRows / 8) * kInChunks * 128;  // 16384
-constexpr uint32_t kA2Bytes = (kTileRows / 8) * kHidChunks * 128; // 28672
-// dynamic shared memory: the weight blob, then one buffer set per tile group (a group = 128 threads that
-// push tiles through the net independently of the other groups of the CTA, sharing only the weights)
+constexpr uint32_t kA2Bytes = (kTileRows / 8) * kHidChunks * 128; // 28672: a 128 x 112 bf16 operand in SHARED memory (masked_policy.cu)
+// dynamic shared memory: the weight blob, then the buffers of the kernel's tile group(s) (a group = 128 threads that push
+// tiles through the net independently of the other groups of the CTA, sharing only the weights); each kernel lays out its
+// own groups — all this file needs is a 16 KB layer-1 A operand (`a1buf`) per tile in flight
 constexpr uint32_t kSmemBlob = 0, kSmemGroups = (kBlobBytes + 127) / 128 * 128;
-constexpr uint32_t kGA1 = 0, kGA2 = kGA1 + kA1Bytes, kGRows = kGA2 + kA2Bytes;             // kGRows: bf16 [12][48] staged decisions
-constexpr uint32_t kGObs = kGRows + kDecPerTile * kIn * 2;                                  // int8 [12][47] (+ pad)
-constexpr uint32_t kGroupBytes = (kGObs + kDecPerTile * kObs + 12 + 127) / 128 * 128;       // 46848
-constexpr uint32_t kTmemColsPerGroup = 128;
-__host__ __device__ constexpr uint32_t policy_smem_bytes(int groups) { return kSmemGroups + (uint32_t)groups * kGroupBytes; }
+// Tensor-memory columns of one tile group: layer 1 accumulates into [0, 112); epilogue 1 compacts them IN PLACE to layer 2's
+// A operand, bf16 pairs in [0, 56) (column j is written after columns 2 j, 2 j + 1 have been read); layer 2 accumulates
+// into [56, 168), whose first 56 columns are layer 1's, all read by then.
+constexpr uint32_t kTmemA2Cols = kHidPad / 2, kTmemAcc2 = kTmemA2Cols, kTmemColsPerGroup = kTmemAcc2 + kHidPad;   // 56, 56, 168
 
 // Barrier over the 128 threads of one tile group (named barrier `id`; id 0 with a single group is __syncthreads).
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kTileRows) : "memory"); }
@@ -92,37 +97,54 @@ struct PhaseClock {
 };
 
 // Once per kernel: the constant chunks (features 48..63) of this thread's row of the layer-1 A operand.
-__device__ __forceinline__ void init_feature_constants(uint8_t* gbuf, int row) {
-    *reinterpret_cast<uint4*>(gbuf + kGA1 + canon_off(row, kBiasCol, kInChunks)) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // 1.0, 1.0, 0 ..
-    *reinterpret_cast<uint4*>(gbuf + kGA1 + canon_off(row, kBiasCol + 8, kInChunks)) = make_uint4(0u, 0u, 0u, 0u);
-    // layer 2's A operand, k = 104..111: hidden units that do not exist.  The epilogue never reads or writes them.
-    *reinterpret_cast<uint4*>(gbuf + kGA2 + canon_off(row, kHidPad - 8, kHidChunks)) = make_uint4(0u, 0u, 0u, 0u);
+__device__ __forceinline__ void init_feature_constants(uint8_t* a1buf, int row) {
+    *reinterpret_cast<uint4*>(a1buf + canon_off(row, kBiasCol, kInChunks)) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // 1.0, 1.0, 0 ..
+    *reinterpret_cast<uint4*>(a1buf + canon_off(row, kBiasCol + 8, kInChunks)) = make_uint4(0u, 0u, 0u, 0u);
 }
 // Chunk c (features 8 c .. 8 c + 7, bf16) of one row of the layer-1 A operand.
-__device__ __forceinline__ void store_feature_chunk(uint8_t* gbuf, int row, int c, uint4 v) {
-    *reinterpret_cast<uint4*>(gbuf + kGA1 + canon_off(row, 0, kInChunks) + c * 128) = v;
+__device__ __forceinline__ void store_feature_chunk(uint8_t* a1buf, int row, int c, uint4 v) {
+    *reinterpret_cast<uint4*>(a1buf + canon_off(row, 0, kInChunks) + c * 128) = v;
 }
 
 // See mlp_tile's while_mma1: marks a value as needed at this point of the instruction stream.
 __device__ __forceinline__ void pin_result(float& x) { asm volatile("" : "+f"(x)); }
 
-// Epilogue 1 for hidden chunks [C0, C1) of 16 columns: TMEM -> ReLU -> bf16 -> layer 2's A operand.
-// The chunk's TMEM loads are all issued before the single wait, so their latencies overlap.
+// ReLU epilogue for hidden chunks [C0, C1) of 16 columns: TMEM -> max(x, 0) -> bf16 pairs -> TMEM, 16 accumulator columns at
+// `src` into 8 operand columns at `dst`.  The chunk group's loads are all issued before the single wait, so their latencies
+// overlap — and so that, when dst == src, every column a store overwrites has been read (in-place compaction: kTmemA2Cols).
 template <int C0, int C1>
-__device__ __forceinline__ void epilogue1_chunks(uint32_t lane_taddr, uint8_t* a2_row) {
+__device__ __forceinline__ void relu_chunks_to_operand(uint32_t src, uint32_t dst) {
     uint32_t v[C1 - C0][16];
 #pragma unroll
-    for (int c = C0; c < C1; ++c) tmem_ld16(lane_taddr + c * 16, v[c - C0]);
+    for (int c = C0; c < C1; ++c) tmem_ld16(src + c * 16, v[c - C0]);
     tmem_ld_wait();
 #pragma unroll
     for (int c = C0; c < C1; ++c) {
         uint32_t packed[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) packed[i] = relu_pack_bf16x2(__uint_as_float(v[c - C0][2 * i]), __uint_as_float(v[c - C0][2 * i + 1]));
-        uint8_t* dst = a2_row + c * 256;   // canon_off(row, 16 c, .) = canon_off(row, 0, .) + 2 chunks of 128 B per c
-        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        tmem_st8(dst + c * 8, packed);
     }
+}
+
+// A whole accumulator row (this thread's TMEM lane, 112 columns at `src`) -> the next layer's A operand (56 columns at `dst`;
+// dst == src or disjoint from it).  4 + 2 chunks + a half bound the live registers.  TMEM reads are the scarce resource of
+// the tile (64 B/clk per SM sub-partition): only the 104 columns that exist are read; units 100, 101 are the constant-1 units
+// that carry the next layer's bias, k = 104..111 do not exist and are written as zeros.  Ends with the wait that makes the
+// stores visible to a tcgen05.mma issued after the next barrier.
+__device__ __forceinline__ void relu_to_operand(uint32_t src, uint32_t dst) {
+    relu_chunks_to_operand<0, 4>(src, dst);
+    relu_chunks_to_operand<4, 6>(src, dst);
+    uint32_t v[8];
+    tmem_ld8(src + 96, v);
+    tmem_ld_wait();
+    uint32_t packed[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) packed[i] = relu_pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+#pragma unroll
+    for (int i = 4; i < 8; ++i) packed[i] = 0u;
+    tmem_st8(dst + 48, packed);
+    tmem_st_wait();
 }
 
 // Epilogue 2 + layer 3 for hidden chunks [C0, C1): part += (w3 / 2) . |acc|, four independent chains.  relu(h) is
@@ -142,15 +164,16 @@ __device__ __forceinline__ void epilogue2_chunks(uint32_t lane_taddr, const floa
 }
 
 // One 128-row tile through the three layers.  The 128 threads of a tile group call this together.
-//   blob: the weights; gbuf: the group's buffers, whose A1 operand the caller has filled (chunks 0..5 per
-//   tile, the constant chunks once); tmem_base: the group's 128 accumulator columns; tid: 0..127 within the
-//   group; bar_id: the group's named barrier; while_mma1(token = 0): work the caller wants done while layer 1's MMAs
-//   run (the threads would only poll the mbarrier).  Returns this thread's row's logit.
-template <class F>
-__device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, uint32_t tmem_base, uint64_t* bar, uint32_t& phase, int tid,
-                                          int bar_id, PhaseClock& pc, F while_mma1) {
-    const int row = tid, warp = tid >> 5;
-    const uint32_t a1 = smem_u32(gbuf + kGA1), a2 = smem_u32(gbuf + kGA2);
+//   blob: the weights; a1buf: the tile's layer-1 A operand, filled by the caller (chunks 0..5 per tile, the constant chunks
+//   once); tmem_base: the group's kTmemColsPerGroup tensor-memory columns; tid: 0..127 within the group; bar_id: the group's
+//   named barrier; while_mma1(token = 0), while_mma2(): work the caller wants done while layer 1's / layer 2's MMAs run (the
+//   threads would only sleep on the mbarrier) — the search kernel draws its Gumbel variates there, the batched kernel stages
+//   and builds the NEXT tile's rows.  A group barrier lies between the two.  Returns this thread's row's logit.
+template <class F1, class F2>
+__device__ __forceinline__ float mlp_tile(const uint8_t* blob, const uint8_t* a1buf, uint32_t tmem_base, uint64_t* bar, uint32_t& phase, int tid,
+                                          int bar_id, PhaseClock& pc, F1 while_mma1, F2 while_mma2) {
+    const int warp = tid >> 5;
+    const uint32_t a1 = smem_u32(a1buf);
     const uint32_t w1 = smem_u32(blob + kOffW1), w2 = smem_u32(blob + kOffW2);
     const float* w3 = reinterpret_cast<const float*>(blob + kOffW3);
     const float b3 = *reinterpret_cast<const float*>(blob + kOffB3);
@@ -180,44 +203,34 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, uint8_t* gbuf, ui
     phase ^= 1u;
     tc_fence_after_sync();
     pc.mark(2);
-    // epilogue 1: ReLU, round to bf16, store as layer 2's A operand (4 + 3 chunks bound the live registers)
-    // TMEM reads are the scarce resource of this tile (64 B/clk per SM): only the 104 columns that exist are read
-    epilogue1_chunks<0, 4>(lane_taddr, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
-    epilogue1_chunks<4, 6>(lane_taddr, gbuf + kGA2 + canon_off(row, 0, kHidChunks));
-    {
-        uint32_t v[8];   // units 96..103 (100, 101 are the constant-1 units that carry b2)
-        tmem_ld8(lane_taddr + 96, v);
-        tmem_ld_wait();
-        uint32_t packed[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) packed[i] = relu_pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-        *reinterpret_cast<uint4*>(gbuf + kGA2 + canon_off(row, 96, kHidChunks)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    }
-    // ---- layer 2 ----
-    fence_async_smem();
+    // epilogue 1: ReLU, round to bf16, back into tensor memory as layer 2's A operand
+    relu_to_operand(lane_taddr, lane_taddr);
+    // ---- layer 2: A from tensor memory ----
     tc_fence_before_sync();
     pc.mark(3);
-    group_sync(bar_id);          // every lane's accumulator has been read: TMEM may be overwritten
+    group_sync(bar_id);          // every lane's operand row is written and its accumulator read: columns 56.. may be overwritten
     pc.mark(4);
     if (tid == 0) {
         tc_fence_after_sync();
 #pragma unroll
         for (int ks = 0; ks < kHidPad / 16; ++ks)
-            umma_bf16(tmem_base, umma_desc(a2 + ks * 256, 128, kHidChunks * 128), umma_desc(w2 + ks * 256, 128, kHidChunks * 128), idesc, ks > 0);
+            umma_bf16_ts(tmem_base + kTmemAcc2, tmem_base + ks * 8, umma_desc(w2 + ks * 256, 128, kHidChunks * 128), idesc, ks > 0);
         umma_commit(bar);
     }
+    while_mma2();
     mbar_wait_mma(bar, phase);
     phase ^= 1u;
     tc_fence_after_sync();
     pc.mark(5);
     // epilogue 2 + layer 3: logit = w3 . relu(acc) + b3 = (linear half from the GEMM) + (w3 / 2) . |acc| + b3, fp32
     float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    epilogue2_chunks<0, 4>(lane_taddr, w3, part);
-    epilogue2_chunks<4, 6>(lane_taddr, w3, part);
+    const uint32_t acc2_taddr = lane_taddr + kTmemAcc2;
+    epilogue2_chunks<0, 4>(acc2_taddr, w3, part);
+    epilogue2_chunks<4, 6>(acc2_taddr, w3, part);
     float linear;
     {
         uint32_t v[8];   // units 96..99: the last ones that exist; units 100..102: the linear half of the head (three terms)
-        tmem_ld8(lane_taddr + 96, v);
+        tmem_ld8(acc2_taddr + 96, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) part[i] = fmaf(fabsf(__uint_as_float(v[i])), w3[96 + i], part[i]);
