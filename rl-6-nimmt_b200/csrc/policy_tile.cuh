@@ -163,6 +163,24 @@ __device__ __forceinline__ void epilogue2_chunks(uint32_t lane_taddr, const floa
         for (int i = 0; i < 16; ++i) part[i & 3] = fmaf(fabsf(__uint_as_float(v[c - C0][i])), w3[c * 16 + i], part[i & 3]);
 }
 
+// Epilogue 2 + layer 3 for one row: logit = w3 . relu(acc) + b3 = (linear half from the GEMM) + (w3 / 2) . |acc| + b3, fp32.
+// acc2_taddr: this thread's lane of layer 2's accumulator.  When it returns, every TMEM load has completed.
+__device__ __forceinline__ float head_from_acc2(uint32_t acc2_taddr, const float* w3, float b3) {
+    float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    epilogue2_chunks<0, 4>(acc2_taddr, w3, part);
+    epilogue2_chunks<4, 6>(acc2_taddr, w3, part);
+    float linear;
+    {
+        uint32_t v[8];   // units 96..99: the last ones that exist; units 100..102: the linear half of the head (three terms)
+        tmem_ld8(acc2_taddr + 96, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) part[i] = fmaf(fabsf(__uint_as_float(v[i])), w3[96 + i], part[i]);
+        linear = (__uint_as_float(v[6]) + __uint_as_float(v[5])) + __uint_as_float(v[4]);
+    }
+    return (b3 + linear) + ((part[0] + part[1]) + (part[2] + part[3]));
+}
+
 // One 128-row tile through the three layers.  The 128 threads of a tile group call this together.
 //   blob: the weights; a1buf: the tile's layer-1 A operand, filled by the caller (chunks 0..5 per tile, the constant chunks
 //   once); tmem_base: the group's kTmemColsPerGroup tensor-memory columns; tid: 0..127 within the group; bar_id: the group's
@@ -185,6 +203,9 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, const uint8_t* a1
     tc_fence_before_sync();
     group_sync(bar_id);
     pc.mark(1);
+    // (thread 0 issues from a divergent branch on purpose: the other lanes of its warp run while_mma1 while it sits in the
+    // blocking MMA issue; the warp-uniform form — elected lane + __syncwarp, as the batched kernel's tile warpgroups use — was
+    // measured here and costs the search ~100 cycles per turn)
     if (tid == 0) {
         tc_fence_after_sync();
 #pragma unroll
@@ -222,21 +243,7 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, const uint8_t* a1
     phase ^= 1u;
     tc_fence_after_sync();
     pc.mark(5);
-    // epilogue 2 + layer 3: logit = w3 . relu(acc) + b3 = (linear half from the GEMM) + (w3 / 2) . |acc| + b3, fp32
-    float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    const uint32_t acc2_taddr = lane_taddr + kTmemAcc2;
-    epilogue2_chunks<0, 4>(acc2_taddr, w3, part);
-    epilogue2_chunks<4, 6>(acc2_taddr, w3, part);
-    float linear;
-    {
-        uint32_t v[8];   // units 96..99: the last ones that exist; units 100..102: the linear half of the head (three terms)
-        tmem_ld8(acc2_taddr + 96, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) part[i] = fmaf(fabsf(__uint_as_float(v[i])), w3[96 + i], part[i]);
-        linear = (__uint_as_float(v[6]) + __uint_as_float(v[5])) + __uint_as_float(v[4]);
-    }
-    const float logit = (b3 + linear) + ((part[0] + part[1]) + (part[2] + part[3]));
+    const float logit = head_from_acc2(lane_taddr + kTmemAcc2, w3, b3);
     tc_fence_before_sync();      // ordered before the caller's next barrier / the next tile's MMA
     pc.mark(6);
     return logit;
