@@ -67,6 +67,14 @@ def test_ragged_batches_and_tile_boundaries():
     big = obs.repeat(40, 1)                                  # 10,560 decisions: many tiles per CTA
     out = PL.policy_probs(big, blob)
     assert torch.equal(out, full.repeat(40, 1))
+    # enough tiles per CTA (2, 3, 4, 7, 15, 60 on 148 SMs) that the producers' six-stage operand ring and the three tensor-memory
+    # slots are reused many times, with odd and even tile counts per CTA and a ragged last tile
+    for reps, cut in ((13, 0), (20, 5), (27, 0), (47, 11), (100, 7), (400, 1)):
+        big = obs.repeat(reps, 1)
+        D = big.shape[0] - cut
+        out, logits = PL.policy_probs(big[:D].clone(), blob, want_logits=True)
+        assert torch.equal(out, full.repeat(reps, 1)[:D]), (reps, cut)
+        assert torch.isfinite(logits).all()
 
 
 def test_torch_module_is_state_dict_compatible():
