@@ -346,6 +346,25 @@ def run_ours(args):
     side_ms = statistics.median(event_ms(g_side.replay) for _ in range(7)) / CYCLE
     assert sum(int(e.illegal.any()) for e in envs) == 0
 
+    # ---- also: every batch's whole game (deal -> ten steps) on its OWN stream, the four chains forked off and joined back inside one
+    # graph: consecutive launches of `value`'s single stream belong to different batches and do not depend on each other, so here
+    # one kernel's ramp and drain run under its neighbours and the deals run under the steps ----
+    chains = [torch.cuda.Stream(device=dev) for _ in range(NSETS)]
+    g_four = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_four):
+        cap = torch.cuda.current_stream(dev)
+        for b, st in enumerate(chains):
+            st.wait_stream(cap)
+            with torch.cuda.stream(st):
+                envs[b].reset(seed=envs[b].seed)
+                for t in range(CYCLE // NSETS):
+                    envs[b].step(tapes[b][t])
+        for st in chains:
+            cap.wait_stream(st)
+    g_four.replay()
+    four_ms = statistics.median(event_ms(g_four.replay) for _ in range(7)) / CYCLE
+    assert sum(int(e.illegal.any()) for e in envs) == 0
+
     # ---- step + observe ("report step-only and step+observe separately"; the reference rebuilds all P observations
     # inside every step, env.py:73): the same cycle with k_observe after every step, int8 and fp32 observations ----
     step_obs = {}
@@ -530,7 +549,10 @@ def run_ours(args):
     # batched leaf evaluation: the policy for every seat of 2^18 games (2^20 decisions, ~8.9e6 rows of 48 features)
     obs_all = envs[0].reset(seed=77).observe(dtype=torch.int8).reshape(-1, 47)[: 1 << 20].contiguous()
     PL.policy_probs(obs_all, blob)
-    leaf_ms = statistics.median(event_ms(lambda: PL.policy_probs(obs_all, blob)) for _ in range(3))
+    def leaf_run():
+        for _ in range(5):   # back to back: one launch alone carries ~5 % of launch latency
+            PL.policy_probs(obs_all, blob)
+    leaf_ms = statistics.median(event_ms(leaf_run) for _ in range(3)) / 5
     # the whole self-play loop of configs[3]: 256 games, four PUCT seats sharing one net (mc_max = 200, run.py), every
     # search on chip, one batched imitation step per iteration
     from rl_6_nimmt_b200.play import BatchedGameSession, PolicySeat
@@ -625,6 +647,8 @@ def run_ours(args):
         "clocks": clocks,
         "also": {"k_random_actions_ms": ra_ms, "k_deal_ms": kdeal_ms,
                  "env_steps_per_sec_redeal_on_side_stream": world * B / (side_ms * 1e-3),
+                 "env_steps_per_sec_batches_on_four_streams": world * B / (four_ms * 1e-3),
+                 "batches_on_four_streams_note": "the same 40 steps + 4 re-deals with every batch's game (deal -> ten steps) on its own stream, forked and joined inside one graph: up to four 2^20-game kernels are in flight at once, so this is NOT configs[1]'s one batch at a time — it shows what the ramp and drain of a 23 us launch and the serial deals cost `value`",
                  "redeal_on_side_stream_note": "the timed 40-step cycle with the 4 re-deals issued on a second stream (each batch still deal -> ten steps in order): the instruction-bound deal runs under the other batches' memory-bound steps; `value` keeps everything on one stream",
                  "fused_random_play_env_steps_per_sec": world * B / (fused_ms * 1e-3),
                  "fused_note": "k_step_tiles<4,true>: actions drawn in-kernel (DrunkHamster for every seat), + k_deal every 10th visit; max over ranks",
