@@ -1,9 +1,9 @@
-// policy_tile.cuh — one 128-row tile of the Alpha0.5 policy net on tcgen05 (shared by the batched
-// leaf-evaluation kernel and the policy-rollout kernel).  See policy_kernels.cu for the overview.
+// policy_tile.cuh — one 128-row tile of the Alpha0.5 policy net on tcgen05: the pieces shared by the batched leaf-evaluation
+// kernel (policy_kernels.cu, which arranges them into a warp-specialised pipeline), the masked-policy kernel and the
+// policy-rollout kernel (which calls mlp_tile, the whole tile with one group of 128 threads).  See policy_kernels.cu for the overview.
 //
-// Both kernels are bound by what happens around the MMAs — per-thread instruction latency in the search kernel, shared-memory
-// bandwidth in the batched one (an SS-mode MMA of this shape reads 7.5 KB of operands per 56 tensor cycles, on the same
-// 128 B/clk the threads' stores use) — so the tile is built to keep both small:
+// All three kernels are bound by what happens around the MMAs — the latency of one tile's chain, with one tile in flight in the
+// search kernel and three in the batched one — so the tile is built to leave the threads little:
 //   * biases ride in the GEMMs: features 48, 49 of every row are the constant 1 and carry b1 split into two
 //     bf16 terms (hi + lo, ~16 mantissa bits); layer 1's units 100, 101 are the constant 1 and carry b2 the
 //     same way.  Epilogue 1 is cvt.relu.bf16x2 + store; epilogue 2 is ONE fma per column, because the linear half
@@ -185,8 +185,8 @@ __device__ __forceinline__ float head_from_acc2(uint32_t acc2_taddr, const float
 //   blob: the weights; a1buf: the tile's layer-1 A operand, filled by the caller (chunks 0..5 per tile, the constant chunks
 //   once); tmem_base: the group's kTmemColsPerGroup tensor-memory columns; tid: 0..127 within the group; bar_id: the group's
 //   named barrier; while_mma1(token = 0), while_mma2(): work the caller wants done while layer 1's / layer 2's MMAs run (the
-//   threads would only sleep on the mbarrier) — the search kernel draws its Gumbel variates there, the batched kernel stages
-//   and builds the NEXT tile's rows.  A group barrier lies between the two.  Returns this thread's row's logit.
+//   threads would only sleep on the mbarrier) — the search kernel draws its Gumbel variates there.  A group barrier lies
+//   between the two.  Returns this thread's row's logit.
 template <class F1, class F2>
 __device__ __forceinline__ float mlp_tile(const uint8_t* blob, const uint8_t* a1buf, uint32_t tmem_base, uint64_t* bar, uint32_t& phase, int tid,
                                           int bar_id, PhaseClock& pc, F1 while_mma1, F2 while_mma2) {
