@@ -49,18 +49,19 @@ struct TreeState {
 
 __device__ __forceinline__ float uniform01(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
 constexpr uint16_t kBf16MinusOne = 0xBF80;
-constexpr uint32_t kSearchSmemBytes = kSmemGroups + kA1Bytes;   // the weights + one layer-1 operand
-constexpr uint32_t kSearchTmemCols = 256;   // 168 used (policy_tile.cuh::kTmemColsPerGroup); allocations are powers of two
+constexpr uint32_t kSearchSmemBytes = kSmemGroups + kA1Bytes + kA2TailBytes;   // the weights + one layer-1 operand + the tail of layer 2's
+// tensor memory: 128 + 32 columns (policy_tile.cuh) — three CTAs per SM, which is what lets the 4 x 86 CTAs of a self-play turn
+// (four seats' searches of 256 trees on four streams) run as ONE wave of 148 x 3 = 444 slots instead of two of 296
 
 template <int P>
-__global__ void __launch_bounds__(kTileRows, 1)
+__global__ void __launch_bounds__(kTileRows, 3)   // three CTAs per SM: <= 168 registers
 k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __restrict__ blob, int n_mc, float c_puct, int mode,
                   uint64_t seed, unsigned long long* __restrict__ stats_out, float* __restrict__ root_probs_out) {
     constexpr int T = 12 / P;                      // trees per CTA
     constexpr unsigned kFull = 0xffffffffu;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
-    __shared__ uint32_t tmem_slot;
+    __shared__ uint32_t tmem_slot, tmem_slot_b;
     __shared__ TreeState trees[T];
     __shared__ uint8_t values[128];
 
@@ -71,13 +72,19 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
-    if (threadIdx.x < 32) tmem_alloc(&tmem_slot, kSearchTmemCols);
+    if (threadIdx.x < 32) {
+        tmem_alloc_keep_permit(&tmem_slot, kSearchTmemA);
+        tmem_alloc_keep_permit(&tmem_slot_b, kSearchTmemB);
+        tmem_relinquish_permit();
+    }
     uint8_t* gbuf = smem + kSmemGroups;
+    uint8_t* a2tail = gbuf + kA1Bytes;
     init_feature_constants(gbuf, threadIdx.x);
+    init_a2_tail(a2tail, threadIdx.x);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_base = tmem_slot, tmem_b = tmem_slot_b;
     uint32_t phase = 0;
     PhaseClock pc;
 
@@ -214,7 +221,7 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
             // a draw from softmax(logits), so a sampled move needs no exponentials, no sum and no CDF.  The row's
             // Gumbel variate is computed while the tensor core runs layer 1.
             float gumbel = 0.0f;
-            const float logit = mlp_tile(smem + kSmemBlob, gbuf, tmem_base, &bar, phase, threadIdx.x, 0, pc, [&](uint32_t token) {
+            const float logit = mlp_tile(smem + kSmemBlob, gbuf, a2tail, tmem_base, tmem_b, &bar, phase, threadIdx.x, 0, pc, [&](uint32_t token) {
                 Philox rng(seed, rollout_id, (0x73616d70u + (uint32_t)turn) ^ token, (uint32_t)(player * 16 + slot));
                 const float u = ((float)(rng.next<7>().x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // in (0, 1)
                 gumbel = -__logf(-__logf(u));
@@ -315,7 +322,10 @@ k_policy_rollouts(const nimmt_root* __restrict__ roots, int D, const uint8_t* __
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc(tmem_base, kSearchTmemCols);
+    if (threadIdx.x < 32) {
+        tmem_dealloc(tmem_base, kSearchTmemA);
+        tmem_dealloc(tmem_b, kSearchTmemB);
+    }
 }
 
 // PUCTAgent._compute_pucts / _normalize_q / the choice (agents/mcts.py:276-315) for a batch of decisions whose outcome lists are

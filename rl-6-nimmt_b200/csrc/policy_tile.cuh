@@ -44,6 +44,14 @@ constexpr uint32_t kSmemBlob = 0, kSmemGroups = (kBlobBytes + 127) / 128 * 128;
 // into [56, 168), whose first 56 columns are layer 1's, all read by then.
 constexpr uint32_t kTmemA2Cols = kHidPad / 2, kTmemAcc2 = kTmemA2Cols, kTmemColsPerGroup = kTmemAcc2 + kHidPad;   // 56, 56, 168
 
+// The search kernel's tile (mlp_tile) squeezes into 160 columns — two allocations, 128 + 32, so that THREE of its CTAs share an
+// SM's 512 (one allocation would be 256: two CTAs) — by giving layer 1 and layer 2 the same accumulator columns and parking the
+// operand elsewhere: block A [0, 112) both accumulators (layer 2 starts after epilogue 1 has read layer 1's), block A [112, 128)
+// operand K-chunks 0, 1, block B [0, 32) K-chunks 2..5, and the last K-chunk (units 96..111) in SHARED memory — a tcgen05.mma
+// picks its A operand from either memory per instruction.
+constexpr uint32_t kSearchTmemA = 128, kSearchTmemB = 32, kSearchA2InA = 112;
+constexpr uint32_t kA2TailBytes = (kTileRows / 8) * 2 * 128;   // 4096: a [128 x 16] bf16 operand, canonical layout with two K-chunks
+
 // Barrier over the 128 threads of one tile group (named barrier `id`; id 0 with a single group is __syncthreads).
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kTileRows) : "memory"); }
 
@@ -100,6 +108,11 @@ struct PhaseClock {
 __device__ __forceinline__ void init_feature_constants(uint8_t* a1buf, int row) {
     *reinterpret_cast<uint4*>(a1buf + canon_off(row, kBiasCol, kInChunks)) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // 1.0, 1.0, 0 ..
     *reinterpret_cast<uint4*>(a1buf + canon_off(row, kBiasCol + 8, kInChunks)) = make_uint4(0u, 0u, 0u, 0u);
+}
+// Once per kernel (mlp_tile's callers): hidden units 104..111 of this thread's row of the shared-memory tail of layer 2's A operand
+// do not exist.
+__device__ __forceinline__ void init_a2_tail(uint8_t* a2tail, int row) {
+    *reinterpret_cast<uint4*>(a2tail + canon_off(row, 8, 2)) = make_uint4(0u, 0u, 0u, 0u);
 }
 // Chunk c (features 8 c .. 8 c + 7, bf16) of one row of the layer-1 A operand.
 __device__ __forceinline__ void store_feature_chunk(uint8_t* a1buf, int row, int c, uint4 v) {
@@ -183,20 +196,21 @@ __device__ __forceinline__ float head_from_acc2(uint32_t acc2_taddr, const float
 
 // One 128-row tile through the three layers.  The 128 threads of a tile group call this together.
 //   blob: the weights; a1buf: the tile's layer-1 A operand, filled by the caller (chunks 0..5 per tile, the constant chunks
-//   once); tmem_base: the group's kTmemColsPerGroup tensor-memory columns; tid: 0..127 within the group; bar_id: the group's
+//   once); a2tail: kA2TailBytes of shared memory (init_a2_tail once); tmem_base, tmem_b: the group's two tensor-memory blocks
+//   (kSearchTmemA, kSearchTmemB columns); tid: 0..127 within the group; bar_id: the group's
 //   named barrier; while_mma1(token = 0), while_mma2(): work the caller wants done while layer 1's / layer 2's MMAs run (the
 //   threads would only sleep on the mbarrier) — the search kernel draws its Gumbel variates there.  A group barrier lies
 //   between the two.  Returns this thread's row's logit.
 template <class F1, class F2>
-__device__ __forceinline__ float mlp_tile(const uint8_t* blob, const uint8_t* a1buf, uint32_t tmem_base, uint64_t* bar, uint32_t& phase, int tid,
-                                          int bar_id, PhaseClock& pc, F1 while_mma1, F2 while_mma2) {
+__device__ __forceinline__ float mlp_tile(const uint8_t* blob, const uint8_t* a1buf, uint8_t* a2tail, uint32_t tmem_base, uint32_t tmem_b, uint64_t* bar,
+                                          uint32_t& phase, int tid, int bar_id, PhaseClock& pc, F1 while_mma1, F2 while_mma2) {
     const int warp = tid >> 5;
-    const uint32_t a1 = smem_u32(a1buf);
+    const uint32_t a1 = smem_u32(a1buf), a2t = smem_u32(a2tail);
     const uint32_t w1 = smem_u32(blob + kOffW1), w2 = smem_u32(blob + kOffW2);
     const float* w3 = reinterpret_cast<const float*>(blob + kOffW3);
     const float b3 = *reinterpret_cast<const float*>(blob + kOffB3);
     constexpr uint32_t idesc = umma_idesc_bf16(kTileRows, kHidPad);
-    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16), lane_b = tmem_b + ((uint32_t)(warp * 32) << 16);
 
     // ---- layer 1 ----
     fence_async_smem();          // the caller's feature stores -> visible to the tensor-core (async) proxy
@@ -224,18 +238,33 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, const uint8_t* a1
     phase ^= 1u;
     tc_fence_after_sync();
     pc.mark(2);
-    // epilogue 1: ReLU, round to bf16, back into tensor memory as layer 2's A operand
-    relu_to_operand(lane_taddr, lane_taddr);
-    // ---- layer 2: A from tensor memory ----
+    // epilogue 1: ReLU, round to bf16; K-chunks 0, 1 of layer 2's A operand into block A behind the accumulator, 2..5 into block B,
+    // the last one (units 96..103; 104..111 are zeros written once, init_a2_tail) into shared memory
+    relu_chunks_to_operand<0, 2>(lane_taddr, lane_taddr + kSearchA2InA);
+    relu_chunks_to_operand<2, 6>(lane_taddr, lane_b - 16);               // chunk c -> lane_b + 8 (c - 2)
+    {
+        uint32_t v[8];
+        tmem_ld8(lane_taddr + 96, v);
+        tmem_ld_wait();
+        uint32_t packed[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) packed[i] = relu_pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        *reinterpret_cast<uint4*>(a2tail + canon_off(tid, 0, 2)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    tmem_st_wait();
+    fence_async_smem();          // the tail chunk -> visible to the tensor core's (async) proxy
+    // ---- layer 2: A from tensor memory (six K-steps) and from shared memory (the last), accumulator over layer 1's ----
     tc_fence_before_sync();
     pc.mark(3);
-    group_sync(bar_id);          // every lane's operand row is written and its accumulator read: columns 56.. may be overwritten
+    group_sync(bar_id);          // every lane's operand row is written and its accumulator read: columns [0, 112) may be overwritten
     pc.mark(4);
     if (tid == 0) {
         tc_fence_after_sync();
 #pragma unroll
-        for (int ks = 0; ks < kHidPad / 16; ++ks)
-            umma_bf16_ts(tmem_base + kTmemAcc2, tmem_base + ks * 8, umma_desc(w2 + ks * 256, 128, kHidChunks * 128), idesc, ks > 0);
+        for (int ks = 0; ks < kHidPad / 16 - 1; ++ks)
+            umma_bf16_ts(tmem_base, ks < 2 ? tmem_base + kSearchA2InA + ks * 8 : tmem_b + (ks - 2) * 8, umma_desc(w2 + ks * 256, 128, kHidChunks * 128), idesc,
+                         ks > 0);
+        umma_bf16(tmem_base, umma_desc(a2t, 128, 2 * 128), umma_desc(w2 + (kHidPad / 16 - 1) * 256, 128, kHidChunks * 128), idesc, 1);
         umma_commit(bar);
     }
     while_mma2();
@@ -243,7 +272,7 @@ __device__ __forceinline__ float mlp_tile(const uint8_t* blob, const uint8_t* a1
     phase ^= 1u;
     tc_fence_after_sync();
     pc.mark(5);
-    const float logit = head_from_acc2(lane_taddr + kTmemAcc2, w3, b3);
+    const float logit = head_from_acc2(lane_taddr, w3, b3);
     tc_fence_before_sync();      // ordered before the caller's next barrier / the next tile's MMA
     pc.mark(6);
     return logit;
