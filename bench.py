@@ -546,6 +546,10 @@ def run_ours(args):
     blob = PL.pack_weights(PL.PolicyNet(), device=dev)
     R.policy_rollouts(roots_d, P, blob, 200, seed=1)
     puct_ms = statistics.median(event_ms(lambda: R.policy_rollouts(roots_d, P, blob, 200, seed=2 + r)) for r in range(3))
+    # the same kernel with every slot of the chip taken: three trees per CTA, three CTAs per SM (256 trees are 86 CTAs on 148 SMs)
+    sat_trees = 3 * 3 * torch.cuda.get_device_properties(dev).multi_processor_count
+    R.policy_rollouts(shard_roots[:sat_trees], P, blob, 200, seed=1)
+    sat_ms = statistics.median(event_ms(lambda: R.policy_rollouts(shard_roots[:sat_trees], P, blob, 200, seed=2 + r)) for r in range(3))
     # batched leaf evaluation: the policy for every seat of 2^18 games (2^20 decisions, ~8.9e6 rows of 48 features)
     obs_all = envs[0].reset(seed=77).observe(dtype=torch.int8).reshape(-1, 47)[: 1 << 20].contiguous()
     PL.policy_probs(obs_all, blob)
@@ -571,6 +575,9 @@ def run_ours(args):
         "policy_tflops_in_search": world * search_tflops,
         "selfplay_games_per_sec": world * 256 / (selfplay_ms * 1e-3), "selfplay_ms_per_256_games": selfplay_ms,
         "selfplay_config": "256 four-player games per GPU, every seat a PUCT agent (mc_max 200) on one shared net, 36 search launches + one batched imitation step (Adam) per iteration",
+        "puct_saturated": {"trees_per_gpu": sat_trees, "ms": sat_ms, "rollouts_per_sec": world * sat_trees * 200 / (sat_ms * 1e-3),
+                           "policy_tflops_per_gpu": sat_trees * 200 * rows_per_rollout * flop_per_row / (sat_ms * 1e-3) / 1e12,
+                           "note": "k_policy_rollouts with all 3 x 148 CTA slots of the chip filled (1,332 searches per GPU): the throughput the kernel has for batches beyond configs[3]'s 256 trees, whose 86 CTAs measure the latency of a search"},
         "leaf_eval_decisions_per_sec": world * (1 << 20) / (leaf_ms * 1e-3),
         "leaf_eval_tflops": world * leaf_tflops,
         "roofline": {"bound": "tensor", "achieved": search_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": search_tflops / peaks["bf16_tflops"],
