@@ -161,36 +161,8 @@ __device__ __forceinline__ void mbar_wait_mma_a(uint32_t bar, uint32_t parity) {
 #endif
 }
 
-// Non-blocking: has the phase with this parity completed?  (The MMA-issuing thread of a warp-specialised kernel polls several
-// barriers and issues whichever layer is ready.)
-__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done;
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { mbar_arrive_a(smem_u32(bar)); }
-// The same on 32-bit shared-memory addresses taken once, outside the polling loop.
-__device__ __forceinline__ uint32_t mbar_test_a(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return done;
-}
+// tcgen05.commit on a 32-bit shared-memory address taken once, outside the loop.
 __device__ __forceinline__ void umma_commit_a(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
