@@ -696,6 +696,22 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         line["mcs"]["cpu_baseline"] = {"value": int(st[:, 2].sum()) / dt, "unit": "rollouts/s", "cores": cores, "kind": "port",
                                        "sample": f"{int(st[:, 2].sum())} reference-law rollouts of a 4-player opening root (determinise + 10 turns, agents/mcts.py:108-154) in {dt:.1f} s on {cores} threads; C port (oracle/nimmt_oracle.c)"}
+        # Alpha0.5's rollout loop (PolicyMCSAgent: every move sampled from softmax(policy net), agents/mcts.py:129-154, 209-228) on the
+        # same host cores: the fp32 C port, one call per thread (ctypes releases the GIL), same net and root as the GPU number
+        from concurrent.futures import ThreadPoolExecutor
+        torch.manual_seed(0)
+        sd = {k: v.detach().cpu().numpy() for k, v in PL.PolicyNet().state_dict().items()}
+        wts = {"w1": sd["latent_net.0.weight"], "b1": sd["latent_net.0.bias"], "w2": sd["latent_net.2.weight"], "b2": sd["latent_net.2.bias"],
+               "w3": sd["head_nets.0.0.weight"], "b3": sd["head_nets.0.0.bias"]}
+        t0 = time.perf_counter()
+        oracle.policy_rollouts(P, board, own, avail, 100, wts, seed=1)
+        per_thread = max(100, int(100 / (time.perf_counter() - t0) * 6))   # ~6 s of CPU work per thread
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as pool:
+            done_rollouts = sum(int(st[:, 2].sum()) for st in pool.map(lambda i: oracle.policy_rollouts(P, board, own, avail, per_thread, wts, seed=10 + i), range(cores)))
+        dt = time.perf_counter() - t0
+        line["alpha05"]["cpu_baseline"] = {"value": done_rollouts / dt, "unit": "rollouts/s", "cores": cores, "kind": "port",
+                                           "sample": f"{done_rollouts} policy-driven rollouts of a 4-player opening root (220 fp32 evaluations of the 48-100-100-1 net each; the root move sampled from the policy, PUCT differs in that move only) in {dt:.1f} s on {cores} threads; C port (oracle/nimmt_oracle.c)"}
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
