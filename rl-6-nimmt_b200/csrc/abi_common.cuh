@@ -123,6 +123,7 @@ inline int blocks_per_sm_cached(Kernel kernel, int threads, int smem, int (&cach
     const int dev = current_device();
     if (cache[dev] == 0) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   // these kernels live in shared memory, not in L1
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
         cache[dev] = occ > 0 ? occ : 1;
