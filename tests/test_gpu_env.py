@@ -294,3 +294,35 @@ def test_reset_to_midgame_positions_from_the_golden_traces(P):
             assert (out[k] == g(k)[:, t0 + 1:]).all(), (k, t0)
         base = g("scores")[:, t0][:, None, :]
         assert (out["scores"] == g("scores")[:, t0 + 1:] - base).all()
+
+
+def test_batches_on_four_streams_equal_one_stream():
+    """The ABI promises re-entrant, enqueue-only calls that are safe on distinct state buffers (threading): four
+    batches dealt and played concurrently, each on its own stream (the shape of bench.py's four-stream figure), end in exactly
+    the states, rewards and flags that the same four batches reach one after the other on one stream."""
+    n, P = (1 << 16) + 32 * 7, 4
+
+    def play(streams):
+        envs = [BatchedSechsNimmtEnv(n, P, seed=300 + b, game0=b * n) for b in range(4)]
+        outs = []
+        for b, env in enumerate(envs):
+            st = streams[b] if streams else torch.cuda.current_stream()
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                env.reset()
+                rews, dones = [], []
+                for t in range(10):
+                    rew, done = env.step(env.random_actions())
+                    rews.append(rew.clone())
+                    dones.append(done.clone())
+                outs.append((torch.stack(rews), torch.stack(dones), env.state.clone(), env.illegal.clone()))
+        torch.cuda.synchronize()
+        return outs
+
+    serial = play(None)
+    for rep in range(2):
+        conc = play([torch.cuda.Stream() for _ in range(4)])
+        for b in range(4):
+            for x, y in zip(serial[b], conc[b]):
+                assert torch.equal(x, y), (rep, b)
+    assert all(bool(o[1][-1].all()) and not bool(o[3].any()) for o in serial)

@@ -163,6 +163,30 @@ def test_puct_search_batch():
     assert (s1[:, int(np.argmax(z["root_probs"])), 2] == 1).all()
 
 
+def test_concurrent_searches_on_four_streams_equal_serial_ones():
+    """A self-play turn launches the four seats' searches on four streams: 4 x 86 CTAs of k_policy_rollouts share the SMs three to
+    one (each CTA holds 128 + 32 tensor-memory columns, allocated in two steps).  A search depends on (seed, tree) only, so the
+    tables of concurrent launches must equal, bit for bit, those of the same launches one after the other."""
+    z, net, w = _rollout_golden()
+    root = R.pack_root_from_state(z["state"], z["legal"].tolist(), z["available"].tolist())
+    blob = PL.pack_weights(net)
+    roots = torch.as_tensor(np.repeat(root[None], 256, axis=0)).cuda()
+    serial = [R.policy_rollouts(roots, 4, blob, 120, c_puct=2.0, root_rule=N.ROOT_PUCT, seed=50 + i)[0].clone() for i in range(4)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    for rep in range(3):
+        got = []
+        for i, st in enumerate(streams):
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                got.append(R.policy_rollouts(roots, 4, blob, 120, c_puct=2.0, root_rule=N.ROOT_PUCT, seed=50 + i)[0])
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        for i in range(4):
+            assert torch.equal(got[i], serial[i]), (rep, i)
+
+
 def test_alpha05_agent_dropin_plays_and_learns():
     from rl_6_nimmt_b200.agents import DrunkHamster, PUCTAgent
     from rl_6_nimmt_b200.env import SechsNimmtEnv
